@@ -1,0 +1,138 @@
+/*
+ * b200_spmv.h -- C ABI of the `b200` libspmv platform (libb200-spmv.so).
+ *
+ * Part 1 is the drop-in boundary: exactly the two symbols every libspmv
+ * backend of mob-group/lilac-benchmarks exports, so the reference's callers
+ * relink (-lb200-spmv) or dlopen it unchanged.  Part 2 is the resident-matrix
+ * API the drop-in symbols are built on; it takes DEVICE pointers and a CUDA
+ * stream and is what bench.py, the tests and the multi-GPU row-block path
+ * drive.  Plain C types only; no torch types anywhere.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device and aborts
+ * (stderr message + abort(), like the asserts of libspmv/gpu.c:42-80) when
+ * there is none.
+ */
+#ifndef B200_SPMV_H
+#define B200_SPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Part 1 -- the libspmv ABI
+ *
+ * Replaces: libspmv/native.c:3-6   (spmv_harness_, CPU loop)
+ *           libspmv/gpu.c:211-289  (spmv_harness_, cuSPARSE csrmv_mp)
+ *           libspmv/mkl.c:28-75    (spmv_harness_, MKL)
+ * and the fp32 twins native.c:8-11 / gpu.c:291-369.
+ *
+ *   ov      out  y[*rows]                      (overwritten, alpha=1 beta=0)
+ *   a       in   values[nnz]
+ *   iv      in   x[>= max(colidx)]
+ *   rowstr  in   [*rows+1] 1-based offsets, nnz = rowstr[*rows]-rowstr[0]
+ *   colidx  in   [nnz] 1-based column indices, any order, repeats allowed
+ *   rows    in   pointer to the row count (Fortran by-reference)
+ *
+ * The matrix is uploaded on first sight and stays resident in HBM, keyed by
+ * (a, rowstr, colidx, *rows, nnz) like gpu.c:227-262; each call moves only x
+ * (host->device) and y (device->host).  Returns NULL (gpu.c:288); no caller
+ * reads the result.
+ * ---------------------------------------------------------------------- */
+void *spmv_harness_(double *ov, double *a, double *iv,
+                    int *rowstr, int *colidx, int *rows);
+void *f_spmv_harness_(float *ov, float *a, float *iv,
+                      int *rowstr, int *colidx, int *rows);
+
+/* ------------------------------------------------------------------------
+ * Part 2 -- resident-matrix API (new; the reference has no equivalent: its
+ * GPU state is file-static in gpu.c:12-34)
+ * ---------------------------------------------------------------------- */
+
+typedef struct b200_matrix b200_matrix;     /* opaque, one resident CSR (row block) */
+
+/* kernel families */
+enum {
+    B200_KERNEL_AUTO    = 0,  /* chosen from the row-length histogram at upload */
+    B200_KERNEL_ORDERED = 1,  /* nnz-split row blocks, products staged in shared
+                                 memory, each row summed strictly left to right:
+                                 bit-identical to native-impl.c:1-12 */
+    B200_KERNEL_VECTOR  = 2,  /* 2..32 lanes per row + warp-shuffle reduction */
+    B200_KERNEL_PANEL   = 3,  /* ORDERED on the column-panel private layout with
+                                 x slices staged in shared memory (sorted rows) */
+    B200_KERNEL_MERGE   = 4   /* fixed-nnz split with carry-out fix-up for
+                                 heavily skewed row lengths */
+};
+
+enum { B200_F64 = 0, B200_F32 = 1 };
+
+/* Select / initialise the device (-1 = keep cudaGetDevice()).  Optional: every
+ * entry point initialises lazily, as dlopen callers need (pagerank/main.cpp:19). */
+int b200_spmv_init(int device);
+
+/* Upload a 1-based CSR row block from HOST arrays and keep it resident.
+ * `rowstr` points at the block's first row pointer (rows+1 entries); a/colidx
+ * are the bases the offsets refer to, exactly as in the ABI, so a row block
+ * of a larger matrix is (a, colidx, rowstr + row_lo, row_hi - row_lo).
+ * dtype: B200_F64 / B200_F32.  kernel: B200_KERNEL_*.  Aborts on error. */
+b200_matrix *b200_spmv_upload(const void *a, const int *rowstr, const int *colidx,
+                              int rows, int dtype, int kernel);
+void b200_spmv_release(b200_matrix *m);
+
+/* y[0..rows) = A x on `stream` (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream).  d_x, d_y are DEVICE pointers of the matrix dtype;
+ * d_x must hold at least b200_spmv_ncols(m) elements.  Asynchronous. */
+int b200_spmv_exec(b200_matrix *m, const void *d_x, void *d_y, void *stream);
+
+int         b200_spmv_rows(const b200_matrix *m);
+int         b200_spmv_ncols(const b200_matrix *m);   /* max(colidx) */
+int64_t     b200_spmv_nnz(const b200_matrix *m);
+int         b200_spmv_kernel(const b200_matrix *m);  /* family actually chosen */
+const char *b200_spmv_kernel_name(const b200_matrix *m);
+int         b200_spmv_launches_per_exec(const b200_matrix *m);
+/* algorithmic bytes of one product: 12 nnz + 4 (rows+1) + 8 ncols + 8 rows for
+ * fp64, 8/4/4/4 for fp32 */
+int64_t     b200_spmv_algorithmic_bytes(const b200_matrix *m);
+/* bytes the resident private layout occupies in HBM */
+int64_t     b200_spmv_resident_bytes(const b200_matrix *m);
+
+/* row-length histogram gathered at upload: bin k counts rows with
+ * 2^(k-1) < len <= 2^k (bin 0: empty rows and len 1), 32 bins */
+void b200_spmv_row_histogram(const b200_matrix *m, int64_t bins[32],
+                             int *min_len, int *max_len);
+
+/* nnz-balanced contiguous row partition: writes
+ * parts+1 boundaries into `bounds` so that every part holds ~nnz/parts. */
+void b200_spmv_partition_rows(const int *rowstr, int rows, int parts, int *bounds);
+
+/* Resident cache of the drop-in symbols */
+void b200_spmv_invalidate(void);   /* forget every cached matrix (host arrays changed) */
+
+typedef struct {
+    uint64_t calls;            /* ABI calls served */
+    uint64_t uploads;          /* matrix uploads (cache misses) */
+    uint64_t kernel_launches;  /* SpMV kernels launched by the ABI calls */
+    double   kernel_ms;        /* CUDA-event time of those kernels */
+    double   e2e_ms;           /* wall time inside the ABI calls, uploads excluded */
+    double   upload_ms;        /* wall time of the uploads */
+    uint64_t h2d_bytes;        /* x traffic */
+    uint64_t d2h_bytes;        /* y traffic */
+} b200_spmv_stats;
+void b200_spmv_get_stats(b200_spmv_stats *out);
+void b200_spmv_reset_stats(void);
+
+/* Pin a caller-owned host vector so x / y move by direct DMA instead of the
+ * library's pinned bounce buffer.  Only for buffers that outlive the library
+ * use (NPB's COMMON vectors, pagerank's two std::vectors). */
+int b200_spmv_pin_host(void *ptr, size_t bytes);
+int b200_spmv_unpin_host(void *ptr);
+
+const char *b200_spmv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SPMV_H */

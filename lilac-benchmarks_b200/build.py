@@ -1,0 +1,51 @@
+"""Build helper: compiles every native artefact in-tree with `make`.
+
+  csrc/b200.so                 the product (nvcc, sm_100a)
+  callers/libb200callers.so    NPB makea + CG driver (gcc)
+  oracle/liboracle.so, oracle/_ref/*   the checker (gcc; never loaded by the product)
+"""
+import os
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+CALLERS = PKG / "callers"
+ORACLE = ROOT / "oracle"
+
+B200_SO = CSRC / "b200.so"
+CALLERS_SO = CALLERS / "libb200callers.so"
+ORACLE_SO = ORACLE / "liboracle.so"
+REF_NATIVE_SO = ORACLE / "_ref" / "native.so"
+REF_TEST_BIN = ORACLE / "_ref" / "test"
+
+
+def _make(directory, *targets, quiet=True):
+    env = dict(os.environ)
+    env.pop("CC", None)      # the image exports a CC without libgomp
+    env.pop("CXX", None)
+    proc = subprocess.run(["make", "-C", str(directory), *targets], env=env,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"make -C {directory} {' '.join(targets)} failed:\n{proc.stdout}")
+    if not quiet:
+        print(proc.stdout)
+    return proc.stdout
+
+
+def build_product(quiet=True):
+    return _make(CSRC, "b200.so", quiet=quiet)
+
+
+def build_callers(quiet=True):
+    return _make(CALLERS, "libb200callers.so", "cg", quiet=quiet)
+
+
+def build_oracle(quiet=True):
+    return _make(ORACLE, "all", quiet=quiet)
+
+
+def build_all(quiet=True):
+    out = build_product(quiet) + build_callers(quiet) + build_oracle(quiet)
+    return out

@@ -1,0 +1,594 @@
+/*
+ * b200_host.cu -- host layer of libb200-spmv.so: the libspmv ABI on top of a
+ * device-resident matrix cache.  Thin C-style code over the CUDA runtime only
+ * (no cuSPARSE, no cuBLAS, no CPU fallback).
+ *
+ * Reference behaviour mirrored (and where it deliberately differs):
+ *   libspmv/gpu.c:36-85    setup(): lazy one-time init, device buffers sized
+ *                          from (rows, cols, nnz).  Here buffers belong to a
+ *                          cache entry and are freed on eviction (gpu.c leaks
+ *                          the old ones on every shape change).
+ *   libspmv/gpu.c:213-223  column count = max(colidx); gpu.c scans the host
+ *                          array with an off-by-one loop, here a device
+ *                          reduction over the uploaded colidx does it.
+ *   libspmv/gpu.c:227-262  matrix kept resident, keyed by the host pointers;
+ *                          here the key also carries rows and nnz, and several
+ *                          matrices can be resident at once.
+ *   libspmv/gpu.c:140-209  mprotect/SIGSEGV invalidation: not installed (no
+ *                          in-scope caller mutates its matrix); replaced by
+ *                          b200_spmv_invalidate() and an optional sampled
+ *                          fingerprint check (B200_SPMV_VALIDATE=1).
+ *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but through
+ *                          pinned staging (or direct DMA when the caller's
+ *                          vector is already pinned) on the library's stream.
+ *   libspmv/gpu.c:42-80    errors: assert -> here message on stderr + abort().
+ */
+#include "../../include/b200_spmv.h"
+#include "spmv_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <vector>
+
+using namespace b200;
+
+#define B200_VERSION "b200-spmv 0.1 (sm_100a)"
+
+/* ------------------------------------------------------------------------ */
+static void die(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "libb200-spmv: fatal: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    abort();
+}
+
+#define CUDA_OK(call)                                                          \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess)                                                 \
+            die("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                cudaGetErrorString(e_));                                       \
+    } while (0)
+
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+/* ------------------------------------------------------------------------
+ * resident matrix
+ * ---------------------------------------------------------------------- */
+struct b200_matrix {
+    int dtype;                 /* B200_F64 / B200_F32 */
+    int kernel;                /* family in use */
+    int lanes;                 /* VECTOR: lanes per row */
+    int device;
+    int rows, ncols;
+    int64_t nnz;
+    DevCsr dev;                /* device pointers */
+    void *d_val; int *d_col; int *d_rowptr; int *d_rowblk;
+    int64_t resident_bytes;
+    UploadScan scan;
+    /* staging owned by the drop-in path (allocated lazily) */
+    void *d_x, *d_y;           /* device vectors */
+    void *h_x, *h_y;           /* pinned bounce buffers */
+    size_t x_bytes, y_bytes;
+};
+
+static size_t elem_size(int dtype) { return dtype == B200_F32 ? 4 : 8; }
+
+/* global state ----------------------------------------------------------- */
+struct CacheEntry {
+    const void *a; const int *rowstr; const int *colidx;
+    int rows; int64_t nnz; int dtype;
+    uint64_t fingerprint;
+    uint64_t last_use;
+    b200_matrix *m;
+};
+
+struct PinnedRange { char *lo, *hi; bool ours; };
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static bool g_ready = false;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static std::vector<CacheEntry> g_cache;
+static std::vector<PinnedRange> g_pinned;
+static uint64_t g_tick = 0;
+static b200_spmv_stats g_stats;
+static int g_validate = 0, g_verbose = 0, g_cache_cap = 4, g_time_kernels = 1;
+
+static void dump_stats_at_exit(void)
+{
+    if (!env_int("B200_SPMV_STATS", 0)) return;
+    fprintf(stderr,
+            "libb200-spmv stats: calls=%llu uploads=%llu launches=%llu kernel_ms=%.3f "
+            "e2e_ms=%.3f upload_ms=%.3f h2d_MB=%.3f d2h_MB=%.3f\n",
+            (unsigned long long)g_stats.calls, (unsigned long long)g_stats.uploads,
+            (unsigned long long)g_stats.kernel_launches, g_stats.kernel_ms, g_stats.e2e_ms,
+            g_stats.upload_ms, g_stats.h2d_bytes / 1e6, g_stats.d2h_bytes / 1e6);
+}
+
+static void ensure_init_locked(int device)
+{
+    if (g_ready) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        die("no CUDA device available (%s); this platform has no CPU fallback",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) device = env_int("B200_SPMV_DEVICE", -1);
+    if (device >= 0) CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaGetDevice(&g_device));
+    CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&g_ev0));
+    CUDA_OK(cudaEventCreate(&g_ev1));
+    g_validate = env_int("B200_SPMV_VALIDATE", 0);
+    g_verbose = env_int("B200_SPMV_VERBOSE", 0);
+    g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
+    g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
+    memset(&g_stats, 0, sizeof g_stats);
+    atexit(dump_stats_at_exit);
+    g_ready = true;
+}
+
+/* ------------------------------------------------------------------------
+ * upload
+ * ---------------------------------------------------------------------- */
+static int kernel_from_env(int requested)
+{
+    if (requested != B200_KERNEL_AUTO) return requested;
+    const char *v = getenv("B200_SPMV_KERNEL");
+    if (!v || !*v) return B200_KERNEL_AUTO;
+    if (!strcmp(v, "ordered")) return B200_KERNEL_ORDERED;
+    if (!strcmp(v, "vector")) return B200_KERNEL_VECTOR;
+    if (!strcmp(v, "panel")) return B200_KERNEL_PANEL;
+    if (!strcmp(v, "merge")) return B200_KERNEL_MERGE;
+    if (!strcmp(v, "auto")) return B200_KERNEL_AUTO;
+    die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|merge", v);
+    return 0;
+}
+
+/* greedy nnz-split: consecutive rows are packed into a block until the next
+ * row would overflow the tile (or the row cap); a row longer than the tile
+ * forms a block of its own. */
+static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<int> &blk)
+{
+    blk.clear();
+    blk.push_back(0);
+    const int cap = tile - 2;          /* slack for the 16-byte aligned start */
+    int r = 0;
+    while (r < rows) {
+        const int start = r;
+        const long long base = rowstr[r];
+        long long used = 0;
+        while (r < rows && r - start < kRowsPerBlock) {
+            const long long len = (long long)rowstr[r + 1] - rowstr[r];
+            if (used + len > cap) break;
+            used += len;
+            ++r;
+        }
+        if (r == start) ++r;           /* single long row */
+        (void)base;
+        blk.push_back(r);
+    }
+}
+
+static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *colidx,
+                                  int rows, int dtype, int kernel)
+{
+    if (rows < 0) die("negative row count %d", rows);
+    if (dtype != B200_F64 && dtype != B200_F32) die("unknown dtype %d", dtype);
+    const size_t es = elem_size(dtype);
+    const int base1 = rows > 0 ? rowstr[0] : 1;               /* 1-based offset */
+    const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - base1 : 0;
+    if (nnz < 0) die("rowstr is not non-decreasing (nnz=%lld)", (long long)nnz);
+
+    b200_matrix *m = (b200_matrix *)calloc(1, sizeof *m);
+    m->dtype = dtype;
+    m->rows = rows;
+    m->nnz = nnz;
+    m->device = g_device;
+
+    const size_t nval = (size_t)nnz + kPadElems;
+    CUDA_OK(cudaMalloc(&m->d_val, nval * es));
+    CUDA_OK(cudaMalloc((void **)&m->d_col, nval * sizeof(int)));
+    CUDA_OK(cudaMalloc((void **)&m->d_rowptr, ((size_t)rows + 1) * sizeof(int)));
+    m->resident_bytes = (int64_t)(nval * es + nval * 4 + ((size_t)rows + 1) * 4);
+
+    /* padding: value 0, column 1 (a valid 1-based index) */
+    CUDA_OK(cudaMemsetAsync((char *)m->d_val + (size_t)nnz * es, 0, kPadElems * es, g_stream));
+    {
+        int ones[kPadElems];
+        for (int i = 0; i < kPadElems; ++i) ones[i] = 1;
+        CUDA_OK(cudaMemcpyAsync(m->d_col + nnz, ones, sizeof ones, cudaMemcpyHostToDevice, g_stream));
+        CUDA_OK(cudaStreamSynchronize(g_stream));
+    }
+    if (nnz > 0) {
+        CUDA_OK(cudaMemcpyAsync(m->d_val, (const char *)a + (size_t)(base1 - 1) * es,
+                                (size_t)nnz * es, cudaMemcpyHostToDevice, g_stream));
+        CUDA_OK(cudaMemcpyAsync(m->d_col, colidx + (base1 - 1), (size_t)nnz * sizeof(int),
+                                cudaMemcpyHostToDevice, g_stream));
+    }
+    if (rows > 0) {
+        CUDA_OK(cudaMemcpyAsync(m->d_rowptr, rowstr, ((size_t)rows + 1) * sizeof(int),
+                                cudaMemcpyHostToDevice, g_stream));
+        launch_rebase_rowptr(m->d_rowptr, rows + 1, base1, g_stream);
+    } else {
+        CUDA_OK(cudaMemsetAsync(m->d_rowptr, 0, sizeof(int), g_stream));
+    }
+
+    /* device-side scan: column count, histogram, sortedness */
+    UploadScan *d_scan = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d_scan, sizeof(UploadScan)));
+    launch_upload_scan(m->d_rowptr, m->d_col, rows, (int)nnz, d_scan, g_stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(&m->scan, d_scan, sizeof(UploadScan), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaFree(d_scan));
+    if (nnz == 0) { m->scan.max_col = 0; m->scan.min_col = 1; }
+    if (rows == 0) { m->scan.max_len = 0; m->scan.min_len = 0; }
+    if (m->scan.min_col < 1) die("colidx holds %d; indices are 1-based", m->scan.min_col);
+    m->ncols = m->scan.max_col;
+
+    /* row blocks of the nnz-split kernel (host greedy over the caller's rowstr) */
+    std::vector<int> blk;
+    build_row_blocks(rowstr, rows, tile_elems(dtype == B200_F32), blk);
+    const int nblk = (int)blk.size() - 1;
+    CUDA_OK(cudaMalloc((void **)&m->d_rowblk, blk.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(m->d_rowblk, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m->resident_bytes += (int64_t)(blk.size() * sizeof(int));
+
+    m->dev.val = m->d_val;
+    m->dev.col = m->d_col;
+    m->dev.rowptr = m->d_rowptr;
+    m->dev.rowblk = m->d_rowblk;
+    m->dev.rows = rows;
+    m->dev.nblk = rows > 0 ? nblk : 0;
+    m->dev.nnz = (int)nnz;
+
+    /* kernel choice from the histogram */
+    kernel = kernel_from_env(kernel);
+    if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL || kernel == B200_KERNEL_MERGE)
+        kernel = B200_KERNEL_ORDERED;
+    m->kernel = kernel;
+    {
+        const double mean = rows > 0 ? (double)nnz / rows : 0.0;
+        int lanes = 2;
+        while (lanes < 32 && lanes < mean / 2) lanes *= 2;
+        m->lanes = env_int("B200_SPMV_LANES", lanes);
+    }
+    if (g_verbose)
+        fprintf(stderr,
+                "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
+                "unsorted_rows=%d blocks=%d kernel=%s\n",
+                dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
+                m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
+                b200_spmv_kernel_name(m));
+    return m;
+}
+
+static void release_locked(b200_matrix *m)
+{
+    if (!m) return;
+    cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
+    if (m->d_x) cudaFree(m->d_x);
+    if (m->d_y) cudaFree(m->d_y);
+    if (m->h_x) cudaFreeHost(m->h_x);
+    if (m->h_y) cudaFreeHost(m->h_y);
+    free(m);
+}
+
+static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s)
+{
+    if (m->rows == 0) return 0;
+    if (m->dtype == B200_F64) {
+        if (m->kernel == B200_KERNEL_VECTOR)
+            launch_vector<double>(m->dev, m->lanes, (const double *)d_x, (double *)d_y, s);
+        else
+            launch_ordered<double>(m->dev, (const double *)d_x, (double *)d_y, s);
+    } else {
+        if (m->kernel == B200_KERNEL_VECTOR)
+            launch_vector<float>(m->dev, m->lanes, (const float *)d_x, (float *)d_y, s);
+        else
+            launch_ordered<float>(m->dev, (const float *)d_x, (float *)d_y, s);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) die("kernel launch failed: %s", cudaGetErrorString(e));
+    return 1;
+}
+
+/* ------------------------------------------------------------------------
+ * public resident-matrix API
+ * ---------------------------------------------------------------------- */
+extern "C" int b200_spmv_init(int device)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_init_locked(device);
+    pthread_mutex_unlock(&g_lock);
+    return g_device;
+}
+
+extern "C" b200_matrix *b200_spmv_upload(const void *a, const int *rowstr, const int *colidx,
+                                         int rows, int dtype, int kernel)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_init_locked(-1);
+    b200_matrix *m = upload_locked(a, rowstr, colidx, rows, dtype, kernel);
+    pthread_mutex_unlock(&g_lock);
+    return m;
+}
+
+extern "C" void b200_spmv_release(b200_matrix *m)
+{
+    pthread_mutex_lock(&g_lock);
+    release_locked(m);
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" int b200_spmv_exec(b200_matrix *m, const void *d_x, void *d_y, void *stream)
+{
+    if (!m) die("b200_spmv_exec: null matrix");
+    return exec_locked(m, d_x, d_y, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_rows(const b200_matrix *m) { return m->rows; }
+extern "C" int b200_spmv_ncols(const b200_matrix *m) { return m->ncols; }
+extern "C" int64_t b200_spmv_nnz(const b200_matrix *m) { return m->nnz; }
+extern "C" int b200_spmv_kernel(const b200_matrix *m) { return m->kernel; }
+extern "C" const char *b200_spmv_kernel_name(const b200_matrix *m)
+{
+    switch (m->kernel) {
+    case B200_KERNEL_ORDERED: return "ordered";
+    case B200_KERNEL_VECTOR:  return "vector";
+    case B200_KERNEL_PANEL:   return "panel";
+    case B200_KERNEL_MERGE:   return "merge";
+    default: return "auto";
+    }
+}
+extern "C" int b200_spmv_launches_per_exec(const b200_matrix *m) { return m->rows > 0 ? 1 : 0; }
+extern "C" int64_t b200_spmv_algorithmic_bytes(const b200_matrix *m)
+{
+    const int64_t es = (int64_t)elem_size(m->dtype);
+    return (es + 4) * m->nnz + 4 * ((int64_t)m->rows + 1) + es * m->ncols + es * m->rows;
+}
+extern "C" int64_t b200_spmv_resident_bytes(const b200_matrix *m) { return m->resident_bytes; }
+
+extern "C" void b200_spmv_row_histogram(const b200_matrix *m, int64_t bins[32],
+                                        int *min_len, int *max_len)
+{
+    for (int i = 0; i < 32; ++i) bins[i] = (int64_t)m->scan.hist[i];
+    if (min_len) *min_len = m->scan.min_len;
+    if (max_len) *max_len = m->scan.max_len;
+}
+
+extern "C" void b200_spmv_partition_rows(const int *rowstr, int rows, int parts, int *bounds)
+{
+    const int64_t base = rows > 0 ? rowstr[0] : 0;
+    const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - base : 0;
+    bounds[0] = 0;
+    for (int p = 1; p < parts; ++p) {
+        const int64_t target = base + (nnz * p) / parts;
+        /* first row whose start offset is >= target */
+        const int *it = std::lower_bound(rowstr, rowstr + rows + 1, (int)target);
+        int r = (int)(it - rowstr);
+        if (r > rows) r = rows;
+        if (r < bounds[p - 1]) r = bounds[p - 1];
+        bounds[p] = r;
+    }
+    bounds[parts] = rows;
+}
+
+/* ------------------------------------------------------------------------
+ * drop-in path: cache + per-call x / y movement
+ * ---------------------------------------------------------------------- */
+static uint64_t fingerprint(const void *a, const int *rowstr, const int *colidx,
+                            int rows, int64_t nnz, size_t es)
+{
+    /* sampled FNV-1a over 64 probes of each array: cheap mutation detector */
+    uint64_t h = 1469598103934665603ull;
+    const int base = rows > 0 ? rowstr[0] - 1 : 0;
+    const int probes = 64;
+    for (int k = 0; k < probes && nnz > 0; ++k) {
+        const int64_t i = base + (nnz - 1) * k / (probes - 1);
+        uint64_t v = 0;
+        memcpy(&v, (const char *)a + (size_t)i * es, es);
+        h = (h ^ v) * 1099511628211ull;
+        h = (h ^ (uint64_t)(uint32_t)colidx[i]) * 1099511628211ull;
+    }
+    for (int k = 0; k < probes && rows > 0; ++k) {
+        const int64_t i = (int64_t)rows * k / (probes - 1);
+        h = (h ^ (uint64_t)(uint32_t)rowstr[i]) * 1099511628211ull;
+    }
+    return h;
+}
+
+static bool host_is_pinned(const void *p, size_t bytes)
+{
+    const char *c = (const char *)p;
+    for (const PinnedRange &r : g_pinned)
+        if (c >= r.lo && c + bytes <= r.hi) return true;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *colidx,
+                                  int rows, int dtype)
+{
+    const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - rowstr[0] : 0;
+    ++g_tick;
+    for (CacheEntry &e : g_cache) {
+        if (e.a == a && e.rowstr == rowstr && e.colidx == colidx && e.rows == rows &&
+            e.nnz == nnz && e.dtype == dtype) {
+            if (g_validate &&
+                fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) != e.fingerprint) {
+                if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
+                release_locked(e.m);
+                e = g_cache.back();
+                g_cache.pop_back();
+                break;
+            }
+            e.last_use = g_tick;
+            return e.m;
+        }
+    }
+    /* miss: upload (evict the least recently used entry beyond the cap) */
+    const double t0 = now_ms();
+    if ((int)g_cache.size() >= g_cache_cap) {
+        size_t victim = 0;
+        for (size_t i = 1; i < g_cache.size(); ++i)
+            if (g_cache[i].last_use < g_cache[victim].last_use) victim = i;
+        release_locked(g_cache[victim].m);
+        g_cache[victim] = g_cache.back();
+        g_cache.pop_back();
+    }
+    CacheEntry e;
+    e.a = a; e.rowstr = rowstr; e.colidx = colidx; e.rows = rows; e.nnz = nnz; e.dtype = dtype;
+    e.fingerprint = g_validate ? fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) : 0;
+    e.last_use = g_tick;
+    e.m = upload_locked(a, rowstr, colidx, rows, dtype, B200_KERNEL_AUTO);
+    /* staging for the drop-in path */
+    b200_matrix *m = e.m;
+    m->x_bytes = (size_t)std::max(m->ncols, 1) * elem_size(dtype);
+    m->y_bytes = (size_t)std::max(m->rows, 1) * elem_size(dtype);
+    CUDA_OK(cudaMalloc(&m->d_x, m->x_bytes));
+    CUDA_OK(cudaMalloc(&m->d_y, m->y_bytes));
+    CUDA_OK(cudaMallocHost(&m->h_x, m->x_bytes));
+    CUDA_OK(cudaMallocHost(&m->h_y, m->y_bytes));
+    g_cache.push_back(e);
+    g_stats.uploads++;
+    g_stats.upload_ms += now_ms() - t0;
+    return m;
+}
+
+static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
+                           const int *colidx, const int *rows, int dtype)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_init_locked(-1);
+    CUDA_OK(cudaSetDevice(g_device));
+    const int n = *rows;
+    b200_matrix *m = lookup_locked(a, rowstr, colidx, n, dtype);
+    const double t0 = now_ms();
+    if (n > 0) {
+        /* x: host -> device (gpu.c:264) */
+        if (m->ncols > 0) {
+            if (host_is_pinned(iv, m->x_bytes)) {
+                CUDA_OK(cudaMemcpyAsync(m->d_x, iv, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
+            } else {
+                memcpy(m->h_x, iv, m->x_bytes);
+                CUDA_OK(cudaMemcpyAsync(m->d_x, m->h_x, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
+            }
+        }
+        if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev0, g_stream));
+        const int launched = exec_locked(m, m->d_x, m->d_y, g_stream);
+        if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev1, g_stream));
+        /* y: device -> host (gpu.c:285) */
+        const bool y_pinned = host_is_pinned(ov, m->y_bytes);
+        CUDA_OK(cudaMemcpyAsync(y_pinned ? ov : m->h_y, m->d_y, m->y_bytes,
+                                cudaMemcpyDeviceToHost, g_stream));
+        CUDA_OK(cudaStreamSynchronize(g_stream));
+        if (!y_pinned) memcpy(ov, m->h_y, m->y_bytes);
+        if (g_time_kernels) {
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+            g_stats.kernel_ms += ms;
+        }
+        g_stats.kernel_launches += (uint64_t)launched;
+        g_stats.h2d_bytes += m->ncols > 0 ? m->x_bytes : 0;
+        g_stats.d2h_bytes += m->y_bytes;
+    }
+    g_stats.calls++;
+    g_stats.e2e_ms += now_ms() - t0;
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void *spmv_harness_(double *ov, double *a, double *iv, int *rowstr, int *colidx, int *rows)
+{
+    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F64);
+    return NULL;
+}
+
+extern "C" void *f_spmv_harness_(float *ov, float *a, float *iv, int *rowstr, int *colidx, int *rows)
+{
+    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F32);
+    return NULL;
+}
+
+extern "C" void b200_spmv_invalidate(void)
+{
+    pthread_mutex_lock(&g_lock);
+    for (CacheEntry &e : g_cache) release_locked(e.m);
+    g_cache.clear();
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void b200_spmv_get_stats(b200_spmv_stats *out)
+{
+    pthread_mutex_lock(&g_lock);
+    *out = g_stats;
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void b200_spmv_reset_stats(void)
+{
+    pthread_mutex_lock(&g_lock);
+    memset(&g_stats, 0, sizeof g_stats);
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" int b200_spmv_pin_host(void *ptr, size_t bytes)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_init_locked(-1);
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaSuccess) {
+        PinnedRange r = {(char *)ptr, (char *)ptr + bytes, true};
+        g_pinned.push_back(r);
+    } else {
+        cudaGetLastError();
+    }
+    pthread_mutex_unlock(&g_lock);
+    return e == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int b200_spmv_unpin_host(void *ptr)
+{
+    int rc = -1;
+    pthread_mutex_lock(&g_lock);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+        if (g_pinned[i].lo == (char *)ptr) {
+            cudaHostUnregister(ptr);
+            g_pinned[i] = g_pinned.back();
+            g_pinned.pop_back();
+            rc = 0;
+            break;
+        }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+extern "C" const char *b200_spmv_version(void) { return B200_VERSION; }

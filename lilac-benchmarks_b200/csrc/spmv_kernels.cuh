@@ -1,0 +1,55 @@
+/*
+ * spmv_kernels.cuh -- device-side view of a resident CSR row block and the
+ * launchers of the sm_100a kernel families.
+ * Internal to libb200-spmv; the public surface is include/b200_spmv.h.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+/* tile geometry of the nnz-split (ORDERED) kernel */
+constexpr int kStreamThreads = 256;     /* threads per CTA */
+constexpr int kTileF64       = 4096;    /* products staged per CTA, fp64 (32 KB) */
+constexpr int kTileF32       = 8192;    /* fp32 (32 KB) */
+constexpr int kRowsPerBlock  = 1024;    /* row cap of one row block */
+constexpr int kPadElems      = 16;      /* zero padding behind val / col */
+
+struct DevCsr {
+    const void *val;      /* T[nnz + kPadElems], padding = 0 */
+    const int  *col;      /* int[nnz + kPadElems], 1-based, padding = 1 */
+    const int  *rowptr;   /* int[rows + 1], 0-based offsets into val / col */
+    const int  *rowblk;   /* int[nblk + 1], first row of every row block */
+    int rows;
+    int nblk;
+    int nnz;
+};
+
+/* statistics produced on the device at upload */
+struct UploadScan {
+    int max_col;          /* max(colidx) = number of columns (gpu.c:216-223 intent) */
+    int min_col;          /* must be >= 1 */
+    int max_len;
+    int min_len;
+    int rows_unsorted;    /* rows whose columns are not non-decreasing */
+    int pad;
+    unsigned long long hist[32];
+};
+
+/* y = A x, every row summed left to right (bit-identical to the CPU loop) */
+template <typename T>
+void launch_ordered(const DevCsr &m, const T *x, T *y, cudaStream_t s);
+
+/* y = A x, `lanes` (2..32, power of two) threads per row, shuffle reduction */
+template <typename T>
+void launch_vector(const DevCsr &m, int lanes, const T *x, T *y, cudaStream_t s);
+
+/* upload-time passes */
+void launch_rebase_rowptr(int *rowptr, int rows_plus_1, int base, cudaStream_t s);
+void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
+                        UploadScan *out, cudaStream_t s);
+
+int tile_elems(bool f32);
+
+}  // namespace b200

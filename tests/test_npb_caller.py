@@ -1,0 +1,57 @@
+"""The C restatement of NPB3.3.1/CG/cg.f (callers/npb) on the CPU: matrix
+sizes, zeta verification (cg.f:122-166, 363-392) and the per-iteration history
+printed by the reference's own C twin (SNU_NPB, golden fixture)."""
+import numpy as np
+import pytest
+
+
+def _fmt_rnorm(v):
+    # SNU prints %20.14E, cg.f prints e20.14; compare on the SNU text
+    return f"{v:.14E}"
+
+
+@pytest.mark.parametrize("cls", ["S", "W", "A"])
+def test_makea_sizes_and_structure(npb, npb_history, cls):
+    m = npb.NpbMatrix(cls)
+    assert m.nnz == npb_history["nnz"][cls]
+    assert m.rowstr[0] == 1 and m.rowstr[-1] == m.nnz + 1
+    assert m.colidx.min() >= 1 and m.colidx.max() <= m.n
+    # columns strictly increasing inside every row (cg.f:838-850 keeps them ordered)
+    d = np.diff(m.colidx.astype(np.int64))
+    row_start = np.zeros(m.nnz, dtype=bool)
+    row_start[m.rowstr[1:-1] - 1] = True
+    assert np.all(d[~row_start[1:]] > 0)
+
+
+@pytest.mark.parametrize("cls", ["S", "W", "A"])
+def test_cg_history_matches_reference_c_twin(npb, oracle, npb_history, cls):
+    m = npb.NpbMatrix(cls)
+    res = npb.run_cg(m, oracle.harness_address())
+    assert res["verified"] and res["err"] <= 1e-10
+    assert res["spmv_calls"] == (m.cls.niter + 1) * 26
+    gold = npb_history["classes"][cls]
+    assert [f"{z:.13f}" for z in res["zeta_hist"]] == gold["zeta"]
+    assert [_fmt_rnorm(r) for r in res["rnorm_hist"]] == gold["rnorm"]
+
+
+def test_makea_row_blocks_tile_the_matrix(npb):
+    full = npb.NpbMatrix("S")
+    cuts = [0, 301, 302, 1000, full.n]
+    a, c = [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        part = npb.NpbMatrix("S", lo, hi)
+        assert part.n == hi - lo and part.rowstr[0] == 1
+        assert np.array_equal(np.diff(part.rowstr), np.diff(full.rowstr[lo:hi + 1]))
+        a.append(part.a)
+        c.append(part.colidx)
+    assert np.array_equal(np.concatenate(a), full.a)
+    assert np.array_equal(np.concatenate(c), full.colidx)
+
+
+def test_randlc_first_values(npb):
+    import ctypes as C
+    x = C.c_double(314159265.0)
+    v = npb.lib().npb_randlc(C.byref(x), 1220703125.0)
+    # x1 = a*x0 mod 2^46
+    expect = (314159265 * 1220703125) % (1 << 46)
+    assert x.value == float(expect) and v == expect / float(1 << 46)
