@@ -16,8 +16,9 @@
  *                          matrices can be resident at once.
  *   libspmv/gpu.c:140-209  mprotect/SIGSEGV invalidation: not installed (no
  *                          in-scope caller mutates its matrix); replaced by
- *                          b200_spmv_invalidate() and an optional sampled
- *                          fingerprint check (B200_SPMV_VALIDATE=1).
+ *                          b200_spmv_invalidate() and a sampled fingerprint
+ *                          check of the host arrays on every call (on by
+ *                          default, B200_SPMV_VALIDATE=0 switches it off).
  *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but through
  *                          pinned staging (or direct DMA when the caller's
  *                          vector is already pinned) on the library's stream.
@@ -144,7 +145,7 @@ static void ensure_init_locked(int device)
     CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&g_ev0));
     CUDA_OK(cudaEventCreate(&g_ev1));
-    g_validate = env_int("B200_SPMV_VALIDATE", 0);
+    g_validate = env_int("B200_SPMV_VALIDATE", 1);
     g_verbose = env_int("B200_SPMV_VERBOSE", 0);
     g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
     g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);

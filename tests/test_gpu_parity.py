@@ -1,0 +1,215 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+oracle on the same seeded inputs.  Bit-exact for the order-preserving kernel
+(integer/byte-style bar, because it performs the reference's operations in the
+reference's order); the re-ordering kernels are held to the north star's
+1e-12 relative tolerance on non-cancelling inputs and to 1e-13 of sum|terms|
+on any input."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import make_csr
+
+pytestmark = pytest.mark.gpu
+
+@pytest.fixture(autouse=True)
+def fresh_cache(libspmv):
+    """numpy may hand a freed matrix's address to the next test's arrays; the
+    resident cache is keyed by host pointers, so start every test clean."""
+    libspmv.invalidate()
+    yield
+
+
+REL_TOL_F64 = 1e-12      # north star: per-element relative, fp64
+REL_TOL_F32 = 2e-3       # parboil tools/compare-output:18-25 (0.2 % relative)
+
+
+def _harness(libspmv, a, x, rowstr, colidx, rows=None):
+    rows = len(rowstr) - 1 if rows is None else rows
+    y = np.full(rows, np.nan, dtype=a.dtype)
+    fn = libspmv.f_spmv_harness if a.dtype == np.float32 else libspmv.spmv_harness
+    fn(y, a, x, rowstr, colidx, rows)
+    return y
+
+
+def test_reference_kat_through_the_abi(libspmv, kat):
+    """libspmv/test.cpp:44-54, both precisions, exact equality."""
+    for dt in (np.float64, np.float32):
+        a = np.array(kat["a"], dtype=dt)
+        x = np.array(kat["x"], dtype=dt)
+        rowstr = np.array(kat["rowstr"], dtype=np.int32)
+        colidx = np.array(kat["colidx"], dtype=np.int32)
+        y = _harness(libspmv, a, x, rowstr, colidx, kat["rows"])
+        assert np.array_equal(y, np.array(kat["y"], dtype=dt))
+
+
+def test_reference_test_binary_passes_on_b200_so(libspmv, oracle):
+    """The reference's own unit test (libspmv/test.cpp) dlopens ./b200.so."""
+    if not oracle.REF_TEST_BIN.exists():
+        pytest.skip("oracle/_ref/test not built")
+    proc = subprocess.run([str(oracle.REF_TEST_BIN), "b200"], cwd=str(libspmv.B200_SO.parent),
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert "success!" in proc.stderr, proc.stderr
+
+
+def test_golden_reference_outputs_bit_exact(libspmv, native_vectors):
+    for name, v in native_vectors.items():
+        if "long_row" in name:
+            continue                      # rows longer than a tile are tree-reduced
+        y = _harness(libspmv, v["a"], v["x"], v["rowstr"], v["colidx"])
+        assert np.array_equal(y, v["y"]), name
+
+
+def test_golden_long_rows_within_tolerance(libspmv, oracle, native_vectors):
+    for name, v in native_vectors.items():
+        if "long_row" not in name:
+            continue
+        y = _harness(libspmv, v["a"], v["x"], v["rowstr"], v["colidx"])
+        f32 = v["a"].dtype == np.float32
+        a64, x64 = v["a"].astype(np.float64), v["x"].astype(np.float64)
+        _, mag = oracle.spmv_extended(a64, x64, v["rowstr"], v["colidx"])
+        eps = 6e-8 if f32 else 1.2e-16
+        assert np.all(np.abs(y.astype(np.float64) - v["y"]) <= 64 * eps * mag + 1e-300), name
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [
+    dict(n=1, ncols=1, mean=1), dict(n=7, ncols=3, mean=2), dict(n=1000, ncols=1000, mean=5),
+    dict(n=3000, ncols=500, mean=130), dict(n=64, ncols=20000, mean=1500),
+    dict(n=20000, ncols=20000, mean=1),
+])
+def test_random_matrices_bit_exact(libspmv, oracle, dtype, shape):
+    rng = np.random.default_rng(shape["n"] * 31 + shape["mean"])
+    lens = rng.poisson(shape["mean"], shape["n"])
+    lens[rng.random(shape["n"]) < 0.15] = 0
+    a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=False)
+    y = _harness(libspmv, a, x, rowstr, c)
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+
+
+def test_ragged_edges(libspmv, oracle):
+    rng = np.random.default_rng(11)
+    # all rows empty, rowstr base offset, last column == ncols, x longer than ncols
+    a = np.zeros(0)
+    c = np.zeros(0, dtype=np.int32)
+    rowstr = np.ones(6, dtype=np.int32)
+    assert np.array_equal(_harness(libspmv, a, np.ones(4), rowstr, c), np.zeros(5))
+    lens = rng.integers(0, 9, 200)
+    a, c, rowstr, x = make_csr(rng, 200, 77, lens, base=1234)
+    x_long = np.concatenate([x, rng.standard_normal(50)])
+    assert np.array_equal(_harness(libspmv, a, x_long, rowstr, c), oracle.spmv(a, x, rowstr, c))
+
+
+def test_rows_just_around_the_tile(libspmv, oracle):
+    """Rows of length tile-3 .. tile+1 exercise the block packing limits."""
+    rng = np.random.default_rng(5)
+    for dtype, tile in ((np.float64, 4096), (np.float32, 8192)):
+        lens = [tile - 3, 1, tile - 2, 0, tile - 1, 3, tile, tile + 1, 2]
+        a, c, rowstr, x = make_csr(rng, len(lens), 5000, lens, dtype=dtype, positive=True)
+        y = _harness(libspmv, a, x, rowstr, c)
+        y0 = oracle.spmv(a, x, rowstr, c)
+        short = np.array(lens) <= tile - 2
+        assert np.array_equal(y[short], y0[short])
+        tol = REL_TOL_F64 if dtype == np.float64 else 1e-5
+        assert np.all(np.abs(y - y0) <= tol * np.abs(y0))
+
+
+def test_cache_keys_on_pointers_and_shape(libspmv, oracle):
+    rng = np.random.default_rng(2)
+    libspmv.invalidate()
+    libspmv.reset_stats()
+    a, c, rowstr, x = make_csr(rng, 500, 400, rng.poisson(20, 500))
+    y0 = oracle.spmv(a, x, rowstr, c)
+    for _ in range(5):
+        assert np.array_equal(_harness(libspmv, a, x, rowstr, c), y0)
+    st = libspmv.stats()
+    assert st["uploads"] == 1 and st["calls"] == 5 and st["kernel_launches"] == 5
+    assert st["h2d_bytes"] == 5 * 8 * c.max() and st["d2h_bytes"] == 5 * 8 * 500
+    # a second matrix lives beside the first one
+    a2, c2, rowstr2, x2 = make_csr(rng, 300, 350, rng.poisson(10, 300))
+    assert np.array_equal(_harness(libspmv, a2, x2, rowstr2, c2), oracle.spmv(a2, x2, rowstr2, c2))
+    assert np.array_equal(_harness(libspmv, a, x, rowstr, c), y0)
+    assert libspmv.stats()["uploads"] == 2
+    # explicit invalidation after an in-place change of the values
+    a *= 2.0
+    libspmv.invalidate()
+    assert np.array_equal(_harness(libspmv, a, x, rowstr, c), oracle.spmv(a, x, rowstr, c))
+    assert libspmv.stats()["uploads"] == 3
+
+
+def test_vector_kernel_tolerance(libspmv, oracle):
+    import torch
+    rng = np.random.default_rng(9)
+    a, c, rowstr, x = make_csr(rng, 4000, 3000, rng.poisson(70, 4000), positive=True)
+    y0 = oracle.spmv(a, x, rowstr, c)
+    m = libspmv.ResidentMatrix(a, rowstr, c, kernel="vector")
+    assert m.kernel_name == "vector" and m.ncols == c.max()
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.empty(4000, dtype=torch.float64, device="cuda")
+    m.exec(dx, dy)
+    y = dy.cpu().numpy()
+    nz = y0 != 0
+    assert np.all(np.abs(y - y0)[nz] <= REL_TOL_F64 * np.abs(y0)[nz])
+    # cancelling input: bound against sum|terms| instead
+    a2, c2, rowstr2, x2 = make_csr(rng, 4000, 3000, rng.poisson(70, 4000))
+    m2 = libspmv.ResidentMatrix(a2, rowstr2, c2, kernel="vector")
+    m2.exec(torch.from_numpy(x2).cuda(), dy)
+    _, mag = oracle.spmv_extended(a2, x2, rowstr2, c2)
+    assert np.all(np.abs(dy.cpu().numpy() - oracle.spmv(a2, x2, rowstr2, c2)) <= 1e-13 * mag + 1e-300)
+
+
+def test_resident_matrix_row_block(libspmv, oracle, npb):
+    """A row block is (a, colidx, rowstr + lo, hi - lo): the ABI's own addressing."""
+    import torch
+    m = npb.NpbMatrix("S")
+    x = np.random.default_rng(1).random(m.n)
+    y0 = oracle.spmv(m.a, x, m.rowstr, m.colidx)
+    bounds = libspmv.partition_rows(m.rowstr, 3)
+    dx = torch.from_numpy(x).cuda()
+    parts = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        blk = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, rows=int(hi - lo), row_lo=int(lo))
+        dy = torch.empty(int(hi - lo), dtype=torch.float64, device="cuda")
+        blk.exec(dx, dy)
+        parts.append(dy.cpu().numpy())
+        hist, mn, mx = blk.row_histogram()
+        assert sum(hist) == hi - lo and mn >= 1 and mx <= 127
+    assert np.array_equal(np.concatenate(parts), y0)
+
+
+@pytest.mark.parametrize("cls", ["S", "A"])
+def test_npb_cg_history_bit_identical_to_cpu_run(libspmv, oracle, npb, npb_history, cls):
+    """Whole NPB CG through libb200-spmv: zeta verifies (cg.f:363-368) and --
+    because every product is bit-identical -- the complete ||r|| / zeta
+    history equals the CPU run and the reference C twin's printout."""
+    m = npb.NpbMatrix(cls)
+    gpu = npb.run_cg(m, libspmv.harness_address())
+    assert gpu["verified"] and gpu["spmv_calls"] == (m.cls.niter + 1) * 26
+    cpu = npb.run_cg(m, oracle.harness_address())
+    assert np.array_equal(gpu["zeta_hist"], cpu["zeta_hist"])
+    assert np.array_equal(gpu["rnorm_hist"], cpu["rnorm_hist"])
+    gold = npb_history["classes"][cls]
+    assert [f"{z:.13f}" for z in gpu["zeta_hist"]] == gold["zeta"]
+
+
+def test_class_c_full_size_properties(libspmv, oracle, npb):
+    """BASELINE config 2 at full size: element-wise equality with the (OpenMP)
+    oracle on a seeded x and on the all-ones start vector, linearity in x, and
+    the nnz self-check of the generator."""
+    import torch
+    m = npb.NpbMatrix("C")
+    assert m.n == 150000 and m.nnz == 36121058
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+    assert rm.ncols == m.n and rm.algorithmic_bytes == 12 * m.nnz + 4 * (m.n + 1) + 16 * m.n
+    rng = np.random.default_rng(42)
+    dy = torch.empty(m.n, dtype=torch.float64, device="cuda")
+    for x in (np.ones(m.n), rng.standard_normal(m.n)):
+        rm.exec(torch.from_numpy(x).cuda(), dy)
+        assert np.array_equal(dy.cpu().numpy(), oracle.spmv(m.a, x, m.rowstr, m.colidx, omp=True))
+    # exact scaling by a power of two commutes with every rounding
+    x = rng.standard_normal(m.n)
+    rm.exec(torch.from_numpy(x).cuda(), dy)
+    y1 = dy.cpu().numpy().copy()
+    rm.exec(torch.from_numpy(4.0 * x).cuda(), dy)
+    assert np.array_equal(dy.cpu().numpy(), 4.0 * y1)
