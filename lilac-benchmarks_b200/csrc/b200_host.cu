@@ -90,6 +90,9 @@ struct b200_matrix {
     void *d_val; int *d_col; int *d_rowptr; int *d_rowblk;
     int64_t resident_bytes;
     UploadScan scan;
+    /* PANEL layout (when kernel == B200_KERNEL_PANEL) */
+    DevPanel panel;
+    void *d_pval; uint16_t *d_pcol; uint16_t *d_seglen; int *d_slice_off;
     /* staging owned by the drop-in path (allocated lazily) */
     void *d_x, *d_y;           /* device vectors */
     void *h_x, *h_y;           /* pinned bounce buffers */
@@ -112,6 +115,7 @@ struct PinnedRange { char *lo, *hi; bool ours; };
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static bool g_ready = false;
 static int g_device = -1;
+static int g_sm_count = 148;
 static cudaStream_t g_stream = nullptr;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static std::vector<CacheEntry> g_cache;
@@ -142,6 +146,7 @@ static void ensure_init_locked(int device)
     if (device < 0) device = env_int("B200_SPMV_DEVICE", -1);
     if (device >= 0) CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaGetDevice(&g_device));
+    CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, g_device));
     CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&g_ev0));
     CUDA_OK(cudaEventCreate(&g_ev1));
@@ -194,6 +199,98 @@ static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<
         (void)base;
         blk.push_back(r);
     }
+}
+
+/* Column-panel layout: worth it when x does not fit L1 but the matrix is dense
+ * enough per (row, panel) that staging x slices in shared memory pays:
+ * sorted rows (order-preserving), a handful of panels, >= 4 entries per
+ * (row, panel) on average. */
+static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out)
+{
+    if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
+    if (m->scan.rows_unsorted != 0) return false;
+    const size_t es = elem_size(m->dtype);
+    int wmax = env_int("B200_SPMV_PANEL_COLS", (int)(128 * 1024 / es));
+    wmax = std::min(wmax, 65536);
+    wmax = std::min(wmax, (int)(220 * 1024 / es));
+    if (wmax < 64) return false;
+    const int P = (m->ncols + wmax - 1) / wmax;
+    int W = (m->ncols + P - 1) / P;
+    W = (W + 31) & ~31;
+    if (W > 65536) return false;
+    const double seg = (double)m->nnz / ((double)m->rows * P);
+    if (P > 64 || seg < 4.0) return false;
+    int R = env_int("B200_SPMV_PANEL_ROWS", 0);
+    if (R <= 0) {
+        R = (m->rows + g_sm_count - 1) / g_sm_count;
+        R = (R + 31) & ~31;
+    }
+    R = std::max(32, std::min(1024, (R + 31) & ~31));
+    *P_out = P; *W_out = W; *R_out = R;
+    return true;
+}
+
+static bool build_panel_locked(b200_matrix *m)
+{
+    int P, W, R;
+    if (!panel_applicable(m, &P, &W, &R)) return false;
+    const size_t es = elem_size(m->dtype);
+    const int nblk = (m->rows + R - 1) / R;
+    const int spb = R / 32;
+    const size_t nseg = (size_t)nblk * P * R;
+    const int nslices = nblk * P * spb;
+    int *d_overflow = nullptr, *d_cnt = nullptr;
+    CUDA_OK(cudaMalloc((void **)&m->d_seglen, nseg * sizeof(uint16_t)));
+    CUDA_OK(cudaMemsetAsync(m->d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
+    CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
+    launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, m->d_seglen, d_overflow, g_stream);
+    CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
+    launch_panel_slice_sizes(m->d_seglen, nslices, d_cnt, g_stream);
+    CUDA_OK(cudaGetLastError());
+    int overflow = 0;
+    std::vector<int> cnt((size_t)nslices + 1);
+    CUDA_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaFree(d_overflow));
+    if (overflow) {
+        CUDA_OK(cudaFree(d_cnt));
+        CUDA_OK(cudaFree(m->d_seglen));
+        m->d_seglen = nullptr;
+        return false;
+    }
+    /* exclusive scan of the slice sizes (host; a few 10^4 entries) */
+    long long run = 0;
+    for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
+    cnt[nslices] = (int)run;
+    if (run != m->nnz) die("panel build lost entries: %lld != %lld", run, (long long)m->nnz);
+    m->d_slice_off = d_cnt;
+    CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, g_stream));
+    const size_t nval = (size_t)m->nnz + kPadElems;
+    CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
+    CUDA_OK(cudaMalloc((void **)&m->d_pcol, nval * sizeof(uint16_t)));
+    CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)m->nnz * es, 0, kPadElems * es, g_stream));
+    CUDA_OK(cudaMemsetAsync(m->d_pcol + m->nnz, 0, kPadElems * sizeof(uint16_t), g_stream));
+    DevPanel &pm = m->panel;
+    pm.val = m->d_pval; pm.col = m->d_pcol; pm.seglen = m->d_seglen; pm.slice_off = m->d_slice_off;
+    pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.P = P; pm.W = W; pm.nblk = nblk;
+    if (m->dtype == B200_F64)
+        launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
+                                  (double *)m->d_pval, m->d_pcol, g_stream);
+    else
+        launch_panel_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
+                                 (float *)m->d_pval, m->d_pcol, g_stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    /* the CSR copy of val / col is no longer needed */
+    CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
+    CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
+    m->dev.val = nullptr; m->dev.col = nullptr;
+    m->resident_bytes = (int64_t)(nval * es + nval * 2 + nseg * 2 + ((size_t)nslices + 1) * 4 +
+                                  ((size_t)m->rows + 1) * 4);
+    return true;
 }
 
 static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *colidx,
@@ -271,8 +368,9 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
 
     /* kernel choice from the histogram */
     kernel = kernel_from_env(kernel);
-    if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL || kernel == B200_KERNEL_MERGE)
-        kernel = B200_KERNEL_ORDERED;
+    if (kernel == B200_KERNEL_MERGE) kernel = B200_KERNEL_ORDERED;
+    if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL)
+        kernel = build_panel_locked(m) ? B200_KERNEL_PANEL : B200_KERNEL_ORDERED;
     m->kernel = kernel;
     {
         const double mean = rows > 0 ? (double)nnz / rows : 0.0;
@@ -283,10 +381,10 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d P=%d W=%d]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m));
+                b200_spmv_kernel_name(m), m->panel.R, m->panel.P, m->panel.W);
     return m;
 }
 
@@ -294,6 +392,7 @@ static void release_locked(b200_matrix *m)
 {
     if (!m) return;
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
+    cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_seglen); cudaFree(m->d_slice_off);
     if (m->d_x) cudaFree(m->d_x);
     if (m->d_y) cudaFree(m->d_y);
     if (m->h_x) cudaFreeHost(m->h_x);
@@ -304,7 +403,12 @@ static void release_locked(b200_matrix *m)
 static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s)
 {
     if (m->rows == 0) return 0;
-    if (m->dtype == B200_F64) {
+    if (m->kernel == B200_KERNEL_PANEL) {
+        if (m->dtype == B200_F64)
+            launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
+        else
+            launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+    } else if (m->dtype == B200_F64) {
         if (m->kernel == B200_KERNEL_VECTOR)
             launch_vector<double>(m->dev, m->lanes, (const double *)d_x, (double *)d_y, s);
         else

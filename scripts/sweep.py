@@ -1,0 +1,58 @@
+"""Kernel-only timing sweep over panel geometry / kernel family on one NPB class.
+usage: python scripts/sweep.py C "16384x1024,8192x512,ordered,vector" [iters]"""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as entry  # noqa: E402
+
+entry.load_package()
+from lilac_benchmarks_b200 import libspmv, npb  # noqa: E402
+
+cls = sys.argv[1] if len(sys.argv) > 1 else "C"
+configs = (sys.argv[2] if len(sys.argv) > 2 else "16384x1024,ordered,vector").split(",")
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+m = npb.NpbMatrix(cls)
+rng = np.random.default_rng(0)
+xs = [torch.from_numpy(rng.random(m.n + 2)).cuda() for _ in range(4)]
+y = torch.zeros(m.n, dtype=torch.float64, device="cuda")
+B = 12 * m.nnz + 4 * (m.n + 1) + 16 * m.n
+y_ref = None
+for cfg in configs:
+    env = {}
+    kernel = cfg
+    if "x" in cfg and cfg[0].isdigit():
+        parts = cfg.split("x")
+        env = {"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]}
+        if len(parts) > 2:
+            env["B200_SPMV_PANEL_VARIANT"] = parts[2]
+        kernel = "panel"
+    os.environ.update(env)
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
+    for i in range(10):
+        rm.exec(xs[i & 3], y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        rm.exec(xs[i & 3], y)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    rm.exec(xs[0], y)
+    torch.cuda.synchronize()
+    yy = y.cpu().numpy()
+    if y_ref is None:
+        y_ref = yy.copy()
+    same = bool(np.array_equal(yy, y_ref))
+    print(f"{cls} {cfg:>22s} kernel={rm.kernel_name:8s} {us:9.1f} us  {B / us / 1e3:8.1f} GB/s  "
+          f"frac={B / us / 1e3 / 6533.5:5.3f}  same_as_first={same}", flush=True)
+    rm.release()
+    for k in env:
+        os.environ.pop(k, None)

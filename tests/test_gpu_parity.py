@@ -88,6 +88,62 @@ def test_random_matrices_bit_exact(libspmv, oracle, dtype, shape):
     assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
 
 
+def _exec_resident(libspmv, a, x, rowstr, c, kernel, env=None):
+    import os
+    import torch
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update({k: str(v) for k, v in (env or {}).items()})
+    try:
+        m = libspmv.ResidentMatrix(a, rowstr, c, kernel=kernel)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    tdt = torch.float32 if a.dtype == np.float32 else torch.float64
+    dx = torch.from_numpy(np.ascontiguousarray(x[:max(m.ncols, 1)])).cuda()
+    dy = torch.full((m.rows,), float("nan"), dtype=tdt, device="cuda")
+    m.exec(dx, dy)
+    return m, dy.cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [
+    dict(n=1, ncols=1, mean=1), dict(n=33, ncols=70, mean=9), dict(n=1000, ncols=1000, mean=25),
+    dict(n=5000, ncols=40000, mean=130), dict(n=300, ncols=70000, mean=900),
+    dict(n=2500, ncols=131072, mean=64),
+])
+@pytest.mark.parametrize("panel_env", [
+    {}, {"B200_SPMV_PANEL_COLS": 256, "B200_SPMV_PANEL_ROWS": 64},
+    {"B200_SPMV_PANEL_COLS": 4096, "B200_SPMV_PANEL_ROWS": 1024},
+])
+def test_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, panel_env):
+    """The column-panel layout keeps every row's left-to-right order when the
+    columns are sorted: bit-identical to the reference loop for any panel
+    width / row-block height, including duplicate columns and empty rows."""
+    rng = np.random.default_rng(shape["n"] * 7 + shape["mean"])
+    lens = rng.poisson(shape["mean"], shape["n"])
+    lens[rng.random(shape["n"]) < 0.1] = 0
+    a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=True)
+    y0 = oracle.spmv(a, x, rowstr, c)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "auto", panel_env)
+    if len(c) and m.nnz / (m.rows * max(1, -(-m.ncols // int(panel_env.get("B200_SPMV_PANEL_COLS", 16384))))) >= 4:
+        assert m.kernel_name == "panel", (m.kernel_name, m.ncols, m.nnz)
+    assert np.array_equal(y, y0)
+    # the ordered kernel on the same input agrees too
+    m2, y2 = _exec_resident(libspmv, a, x, rowstr, c, "ordered")
+    assert m2.kernel_name == "ordered" and np.array_equal(y2, y0)
+
+
+def test_panel_falls_back_when_rows_are_unsorted(libspmv, oracle):
+    rng = np.random.default_rng(77)
+    a, c, rowstr, x = make_csr(rng, 2000, 3000, rng.poisson(40, 2000), sort=False)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "panel")
+    assert m.kernel_name == "ordered"
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+
+
 def test_ragged_edges(libspmv, oracle):
     rng = np.random.default_rng(11)
     # all rows empty, rowstr base offset, last column == ncols, x longer than ncols
