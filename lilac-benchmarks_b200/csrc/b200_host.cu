@@ -92,7 +92,7 @@ struct b200_matrix {
     UploadScan scan;
     /* PANEL layout (when kernel == B200_KERNEL_PANEL) */
     DevPanel panel;
-    void *d_pval; uint16_t *d_pcol; uint16_t *d_seglen; int *d_slice_off;
+    void *d_pval; uint16_t *d_pcol; uint16_t *d_perm; int *d_slice_off;
     /* staging owned by the drop-in path (allocated lazily) */
     void *d_x, *d_y;           /* device vectors */
     void *h_x, *h_y;           /* pinned bounce buffers */
@@ -205,27 +205,32 @@ static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<
  * enough per (row, panel) that staging x slices in shared memory pays:
  * sorted rows (order-preserving), a handful of panels, >= 4 entries per
  * (row, panel) on average. */
+static const size_t kSmemMax = 227 * 1024;
+
 static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out)
 {
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
     const size_t es = elem_size(m->dtype);
-    int wmax = env_int("B200_SPMV_PANEL_COLS", (int)(128 * 1024 / es));
-    wmax = std::min(wmax, 65536);
-    wmax = std::min(wmax, (int)(220 * 1024 / es));
-    if (wmax < 64) return false;
-    const int P = (m->ncols + wmax - 1) / wmax;
-    int W = (m->ncols + P - 1) / P;
-    W = (W + 31) & ~31;
-    if (W > 65536) return false;
-    const double seg = (double)m->nnz / ((double)m->rows * P);
-    if (P > 64 || seg < 4.0) return false;
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
-    if (R <= 0) {
-        R = (m->rows + g_sm_count - 1) / g_sm_count;
-        R = (R + 31) & ~31;
-    }
+    if (R <= 0) R = (m->rows + g_sm_count - 1) / g_sm_count;
     R = std::max(32, std::min(1024, (R + 31) & ~31));
+    /* shared memory: 16 B barriers + R sums + nbuf * (W + pad) x entries */
+    const size_t fixed = ((16 + (size_t)R * es + 15) & ~(size_t)15) + 64;
+    const int w_single = std::min<long long>(65504, (long long)((kSmemMax - fixed) / es) - 4) & ~31;
+    const int w_double = std::min<long long>(65504, (long long)((kSmemMax - fixed) / (2 * es)) - 4) & ~31;
+    int P, W;
+    if (m->ncols <= w_single && !getenv("B200_SPMV_PANEL_COLS")) {
+        P = 1;
+        W = (m->ncols + 31) & ~31;
+    } else {
+        int wmax = env_int("B200_SPMV_PANEL_COLS", w_double);
+        wmax = std::max(32, std::min(wmax, w_double)) & ~31;
+        P = (m->ncols + wmax - 1) / wmax;
+        W = (((m->ncols + P - 1) / P) + 31) & ~31;
+    }
+    const double seg = (double)m->nnz / ((double)m->rows * P);
+    if (P > 64 || (seg < 4.0 && P > 1)) return false;
     *P_out = P; *W_out = W; *R_out = R;
     return true;
 }
@@ -237,16 +242,19 @@ static bool build_panel_locked(b200_matrix *m)
     const size_t es = elem_size(m->dtype);
     const int nblk = (m->rows + R - 1) / R;
     const int spb = R / 32;
-    const size_t nseg = (size_t)nblk * P * R;
-    const int nslices = nblk * P * spb;
+    const int ntiles = nblk * P;
+    const size_t nseg = (size_t)ntiles * R;
+    const int nslices = ntiles * spb;
     int *d_overflow = nullptr, *d_cnt = nullptr;
-    CUDA_OK(cudaMalloc((void **)&m->d_seglen, nseg * sizeof(uint16_t)));
-    CUDA_OK(cudaMemsetAsync(m->d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
+    uint16_t *d_seglen = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d_seglen, nseg * sizeof(uint16_t)));
+    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
     CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
-    launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, m->d_seglen, d_overflow, g_stream);
+    launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
+    CUDA_OK(cudaMalloc((void **)&m->d_perm, nseg * sizeof(uint16_t)));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_slice_sizes(m->d_seglen, nslices, d_cnt, g_stream);
+    launch_panel_sort(d_seglen, ntiles, R, m->d_perm, d_cnt, g_stream);
     CUDA_OK(cudaGetLastError());
     int overflow = 0;
     std::vector<int> cnt((size_t)nslices + 1);
@@ -254,36 +262,41 @@ static bool build_panel_locked(b200_matrix *m)
     CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     CUDA_OK(cudaStreamSynchronize(g_stream));
     CUDA_OK(cudaFree(d_overflow));
-    if (overflow) {
-        CUDA_OK(cudaFree(d_cnt));
-        CUDA_OK(cudaFree(m->d_seglen));
-        m->d_seglen = nullptr;
-        return false;
-    }
-    /* exclusive scan of the slice sizes (host; a few 10^4 entries) */
+    /* exclusive scan of the padded slice sizes (host; a few 10^4 entries) */
     long long run = 0;
     for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
+    if (overflow || run > 0x7fffff00LL) {
+        CUDA_OK(cudaFree(d_cnt));
+        CUDA_OK(cudaFree(d_seglen));
+        CUDA_OK(cudaFree(m->d_perm));
+        m->d_perm = nullptr;
+        return false;
+    }
     cnt[nslices] = (int)run;
-    if (run != m->nnz) die("panel build lost entries: %lld != %lld", run, (long long)m->nnz);
     m->d_slice_off = d_cnt;
     CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
                             cudaMemcpyHostToDevice, g_stream));
-    const size_t nval = (size_t)m->nnz + kPadElems;
+    const size_t nval = (size_t)run + 64;
     CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
     CUDA_OK(cudaMalloc((void **)&m->d_pcol, nval * sizeof(uint16_t)));
-    CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)m->nnz * es, 0, kPadElems * es, g_stream));
-    CUDA_OK(cudaMemsetAsync(m->d_pcol + m->nnz, 0, kPadElems * sizeof(uint16_t), g_stream));
+    CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, g_stream));
+    CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
     DevPanel &pm = m->panel;
-    pm.val = m->d_pval; pm.col = m->d_pcol; pm.seglen = m->d_seglen; pm.slice_off = m->d_slice_off;
+    pm.val = m->d_pval; pm.col = m->d_pcol; pm.perm = m->d_perm; pm.slice_off = m->d_slice_off;
     pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.P = P; pm.W = W; pm.nblk = nblk;
+    pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
+    pm.padded = run;
     if (m->dtype == B200_F64)
         launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                  (double *)m->d_pval, m->d_pcol, g_stream);
+                                  d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
     else
         launch_panel_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                 (float *)m->d_pval, m->d_pcol, g_stream);
+                                 d_seglen, (float *)m->d_pval, m->d_pcol, g_stream);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaFree(d_seglen));
+    if (panel_smem_bytes(pm, m->dtype == B200_F32) > kSmemMax)
+        die("panel shared-memory budget exceeded (W=%d R=%d)", W, R);
     /* the CSR copy of val / col is no longer needed */
     CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
     CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
@@ -381,10 +394,10 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d P=%d W=%d]\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d P=%d W=%d padded=%lld]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m), m->panel.R, m->panel.P, m->panel.W);
+                b200_spmv_kernel_name(m), m->panel.R, m->panel.P, m->panel.W, m->panel.padded);
     return m;
 }
 
@@ -392,7 +405,7 @@ static void release_locked(b200_matrix *m)
 {
     if (!m) return;
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
-    cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_seglen); cudaFree(m->d_slice_off);
+    cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_perm); cudaFree(m->d_slice_off);
     if (m->d_x) cudaFree(m->d_x);
     if (m->d_y) cudaFree(m->d_y);
     if (m->h_x) cudaFreeHost(m->h_x);

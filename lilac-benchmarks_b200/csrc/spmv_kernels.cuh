@@ -53,35 +53,32 @@ void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
 int tile_elems(bool f32);
 
 /* ------------------------------------------------------------------------
- * PANEL: private column-panel layout (built once at upload, on the device)
- *
- *   rows are cut into row blocks of R rows (one CTA each, R threads, one row
- *   per thread); columns into P panels of W columns whose x slice fits in
- *   shared memory.  Tile (rb, p) stores, warp slice by warp slice, the
- *   entries of each row that fall into panel p, k-major and compacted
- *   ("ragged": entry k of lane l sits at slice_off + sum_{k'<k} active(k')
- *   + rank of l among the lanes active at k), so a warp reads contiguous
- *   memory while every lane walks its own row left to right.
+ * PANEL: private column-panel layout (built once at upload, on the device);
+ * see spmv_panel.cu for the format.
  * ---------------------------------------------------------------------- */
 struct DevPanel {
-    const void     *val;        /* T[nnz + pad], tile-major ragged order */
-    const uint16_t *col;        /* u16[nnz + pad], 0-based column inside its panel */
-    const uint16_t *seglen;     /* u16[nblk * P * R], entries of (row, panel) */
-    const int      *slice_off;  /* int[nblk * P * R/32 + 1] */
+    const void     *val;        /* T[padded], tile-major SELL-pair order */
+    const uint16_t *col;        /* u16[padded], 0-based column inside its panel; W = +0.0 slot */
+    const uint16_t *perm;       /* u16[nblk * P * R]: sorted position -> row inside the block */
+    const int      *slice_off;  /* int[nblk * P * R/32 + 1], element offsets (multiples of 64) */
     int rows, ncols;
     int R;                      /* rows per row block = threads per CTA (multiple of 32) */
     int P;                      /* number of column panels */
-    int W;                      /* columns per panel */
+    int W;                      /* columns per panel (even) */
     int nblk;                   /* row blocks = CTAs */
+    int use_tma;                /* x slices by cp.async.bulk (else cooperative loads) */
+    long long padded;           /* stored entries including padding */
 };
 
 /* build passes (device side) */
 void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int W, int R,
                         uint16_t *seglen, int *overflow, cudaStream_t s);
-void launch_panel_slice_sizes(const uint16_t *seglen, int nslices, int *slice_cnt, cudaStream_t s);
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, uint16_t *perm,
+                       int *slice_elems, cudaStream_t s);
 template <typename T>
 void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows,
-                       const DevPanel &pm, T *val_out, uint16_t *col_out, cudaStream_t s);
+                       const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
+                       cudaStream_t s);
 /* y = A x on the panel layout; every row summed left to right */
 template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s);

@@ -7,17 +7,34 @@
  * per entry across the L2 fabric; for NPB class C that alone is ~1 cycle per
  * nonzero per SM, more than the HBM roofline allows, and it clogs the
  * load/store pipe for every other access (profiles/r01_run1_*).  A gather
- * from shared memory costs ~6 wavefronts per 32 lanes.  So the matrix is
+ * from shared memory costs ~7 wavefronts per 32 lanes.  So the matrix is
  * re-laid out once, at upload, into (row block x column panel) tiles whose x
- * slice fits in shared memory; the CTA walks the panels left to right, each
- * thread carrying its row's running sum in a register.  With sorted columns
- * (NPB's makea keeps them sorted, cg.f:838-850) this visits every row's
- * entries in their original order, so the result is bit-identical to the
- * reference loop (libspmv/native-impl.c:1-12): separately rounded multiply,
- * separately rounded add, left to right.
+ * slice fits in shared memory; the CTA walks the panels left to right and
+ * every row's running sum is carried from panel to panel.  With sorted
+ * columns (NPB's makea keeps them sorted, cg.f:838-850) this visits every
+ * row's entries in their original order, so the result is bit-identical to
+ * the reference loop (libspmv/native-impl.c:1-12): separately rounded
+ * multiply, separately rounded add, left to right.
  *
- * Algorithmic bytes are unchanged; the private layout stores
- * 16-bit panel-local column indices, so the HBM stream is 10 B per nonzero.
+ * Tile layout (built on the device at upload):
+ *   inside tile (rb, p) the R rows are sorted by their entry count in panel
+ *   p (descending); warp slice w owns sorted positions 32w..32w+31 and is
+ *   stored SELL-style in pairs:  element (k, lane) at
+ *        slice_off + (k/2)*64 + lane*2 + (k%2)
+ *   padded to the slice's longest row rounded up to a pair.  Padding entries
+ *   hold value +0.0 and the panel-local column W, a shared-memory slot that
+ *   always contains +0.0, so they add +0.0 and change no bit of the sum.
+ *   perm[tile][j] maps a sorted position back to its row in the block; the
+ *   running sums live in shared memory between panels.
+ *
+ * Data movement: the matrix stream (8 B value + 2 B panel-local column per
+ * entry) is read with 128-bit / 32-bit coalesced evict-first loads, software
+ * prefetched one chunk ahead and across the panel switch; x slices arrive by
+ * TMA bulk copies (cp.async.bulk + mbarrier) into a double buffer, one panel
+ * ahead of the compute.
+ *
+ * Algorithmic bytes are unchanged; the private layout streams
+ * ~10 B per nonzero plus padding.
  */
 #include "spmv_kernels.cuh"
 
@@ -28,11 +45,46 @@ __device__ __forceinline__ float  pmul(float a, float b)   { return __fmul_rn(a,
 __device__ __forceinline__ double padd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float  padd(float a, float b)   { return __fadd_rn(a, b); }
 
-__device__ __forceinline__ unsigned lanemask_lt()
+template <typename T> struct PairT;
+template <> struct PairT<double> { using type = double2; };
+template <> struct PairT<float>  { using type = float2; };
+
+/* ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) --------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 /* ---- build: entries of every (row, panel) -------------------------------- */
@@ -48,7 +100,7 @@ __global__ void panel_count_kernel(const int *__restrict__ rowptr, const int *__
     for (int i = b; i < e; ++i) {
         const int p = (col[i] - 1) / W;
         while (p_cur < p) {
-            if (cnt > 65535) atomicExch(overflow, 1);
+            if (cnt > 65534) atomicExch(overflow, 1);
             seglen[((size_t)rb * P + p_cur) * R + rr] = (uint16_t)cnt;
             cnt = 0;
             ++p_cur;
@@ -56,7 +108,7 @@ __global__ void panel_count_kernel(const int *__restrict__ rowptr, const int *__
         ++cnt;
     }
     while (p_cur < P) {
-        if (cnt > 65535) atomicExch(overflow, 1);
+        if (cnt > 65534) atomicExch(overflow, 1);
         seglen[((size_t)rb * P + p_cur) * R + rr] = (uint16_t)cnt;
         cnt = 0;
         ++p_cur;
@@ -70,162 +122,267 @@ void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int 
     panel_count_kernel<<<(rows + 127) / 128, 128, 0, s>>>(rowptr, col, rows, P, W, R, seglen, overflow);
 }
 
-/* ---- build: nonzeros of every warp slice --------------------------------- */
-__global__ void panel_slice_sizes_kernel(const uint16_t *__restrict__ seglen, int nslices,
-                                         int *__restrict__ slice_cnt)
+/* ---- build: sort the rows of every tile by entry count ------------------- */
+/* one CTA of 1024 threads per tile; bitonic sort of up to 1024 keys
+ * (count << 16 | 0xFFFF - row) in descending order => longest first, ties by
+ * ascending row. */
+__global__ void __launch_bounds__(1024)
+panel_sort_kernel(const uint16_t *__restrict__ seglen, int R,
+                  uint16_t *__restrict__ perm, int *__restrict__ slice_elems)
 {
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= nslices) return;
-    int v = seglen[(size_t)gw * 32 + lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) slice_cnt[gw] = v;
+    __shared__ uint32_t key[1024];
+    const int tile = blockIdx.x, t = threadIdx.x;
+    key[t] = t < R ? ((uint32_t)seglen[(size_t)tile * R + t] << 16) | (uint32_t)(0xFFFF - t) : 0u;
+    __syncthreads();
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int ixj = t ^ j;
+            if (ixj > t) {
+                const uint32_t a = key[t], b = key[ixj];
+                const bool desc = (t & k) == 0;
+                if (desc ? (a < b) : (a > b)) { key[t] = b; key[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (t < R) {
+        perm[(size_t)tile * R + t] = (uint16_t)(0xFFFF - (key[t] & 0xFFFFu));
+        if ((t & 31) == 0) {
+            const int longest = (int)(key[t] >> 16);
+            slice_elems[tile * (R >> 5) + (t >> 5)] = ((longest + 1) >> 1) * 64;
+        }
+    }
 }
 
-void launch_panel_slice_sizes(const uint16_t *seglen, int nslices, int *slice_cnt, cudaStream_t s)
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, uint16_t *perm,
+                       int *slice_elems, cudaStream_t s)
 {
-    if (nslices <= 0) return;
-    const long long threads = (long long)nslices * 32;
-    panel_slice_sizes_kernel<<<(int)((threads + 255) / 256), 256, 0, s>>>(seglen, nslices, slice_cnt);
+    if (ntiles <= 0) return;
+    panel_sort_kernel<<<ntiles, 1024, 0, s>>>(seglen, R, perm, slice_elems);
 }
 
-/* ---- build: scatter CSR entries into the ragged tile order --------------- */
+/* ---- build: scatter CSR entries into the padded tile order ---------------- */
 template <typename T>
 __global__ void panel_fill_kernel(const T *__restrict__ val, const int *__restrict__ col,
                                   const int *__restrict__ rowptr, int rows, int R, int P, int W,
                                   const uint16_t *__restrict__ seglen,
+                                  const uint16_t *__restrict__ perm,
                                   const int *__restrict__ slice_off, int nslices,
                                   T *__restrict__ val_out, uint16_t *__restrict__ col_out)
 {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   /* global slice id */
     const int lane = threadIdx.x & 31;
     if (gw >= nslices) return;
-    const int spb = R / 32;                   /* slices per (row block, panel) */
+    const int spb = R >> 5;
     const int tile = gw / spb, w = gw - tile * spb;
     const int rb = tile / P, p = tile - rb * P;
-    const int rr = w * 32 + lane;
+    const int rr = perm[(size_t)tile * R + w * 32 + lane];
     const int r = rb * R + rr;
     int len = 0, src = 0;
     if (r < rows) {
-        len = seglen[((size_t)rb * P + p) * R + rr];
+        len = seglen[(size_t)tile * R + rr];
         src = rowptr[r];
         for (int q = 0; q < p; ++q) src += seglen[((size_t)rb * P + q) * R + rr];
     }
-    int off = slice_off[gw];
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    const unsigned lt = lanemask_lt();
-    for (int k = 0; k < maxlen; ++k) {
-        const bool act = k < len;
-        const unsigned m = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            const int idx = off + __popc(m & lt);
-            val_out[idx] = val[src + k];
-            col_out[idx] = (uint16_t)(col[src + k] - 1 - p * W);
+    const int off = slice_off[gw];
+    const int npair = (slice_off[gw + 1] - off) >> 6;
+    for (int kp = 0; kp < npair; ++kp) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 2 * kp + e;
+            T v = (T)0;
+            int c = W;                                     /* the +0.0 slot */
+            if (k < len) {
+                v = val[src + k];
+                c = col[src + k] - 1 - p * W;
+            }
+            const size_t idx = (size_t)off + (size_t)kp * 64 + lane * 2 + e;
+            val_out[idx] = v;
+            col_out[idx] = (uint16_t)c;
         }
-        off += __popc(m);
     }
 }
 
 template <typename T>
 void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows,
-                       const DevPanel &pm, T *val_out, uint16_t *col_out, cudaStream_t s)
+                       const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
+                       cudaStream_t s)
 {
     const int nslices = pm.nblk * pm.P * (pm.R / 32);
     if (nslices <= 0) return;
     const long long threads = (long long)nslices * 32;
     panel_fill_kernel<T><<<(int)((threads + 255) / 256), 256, 0, s>>>(
-        val, col, rowptr, rows, pm.R, pm.P, pm.W, pm.seglen, pm.slice_off, nslices, val_out, col_out);
+        val, col, rowptr, rows, pm.R, pm.P, pm.W, seglen, pm.perm, pm.slice_off, nslices,
+        val_out, col_out);
 }
-template void launch_panel_fill<double>(const double *, const int *, const int *, int,
-                                        const DevPanel &, double *, uint16_t *, cudaStream_t);
-template void launch_panel_fill<float>(const float *, const int *, const int *, int,
-                                       const DevPanel &, float *, uint16_t *, cudaStream_t);
+template void launch_panel_fill<double>(const double *, const int *, const int *, int, const DevPanel &,
+                                        const uint16_t *, double *, uint16_t *, cudaStream_t);
+template void launch_panel_fill<float>(const float *, const int *, const int *, int, const DevPanel &,
+                                       const uint16_t *, float *, uint16_t *, cudaStream_t);
 
 /* ------------------------------------------------------------------------
  * the product
  * ---------------------------------------------------------------------- */
 template <typename T, int U>
+struct Chunk {
+    typename PairT<T>::type v[U];
+    uint32_t c[U];
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT<T>::type *vp,
+                                           const uint32_t *cp, int kp, int npair)
+{
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            ch.v[u] = __ldcs(vp + (size_t)(kp + u) * 32);
+            ch.c[u] = __ldcs(cp + (size_t)(kp + u) * 32);
+        }
+    }
+}
+
+template <typename T, int U>
+__device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T acc, int kp, int npair)
+{
+    T xa[U], xb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            xa[u] = xs[ch.c[u] & 0xFFFFu];
+            xb[u] = xs[ch.c[u] >> 16];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            acc = padd(acc, pmul(ch.v[u].x, xa[u]));
+            acc = padd(acc, pmul(ch.v[u].y, xb[u]));
+        }
+    }
+    return acc;
+}
+
+template <typename T, int U>
 __global__ void __launch_bounds__(1024, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
-                  const uint16_t *__restrict__ seglen, const int *__restrict__ slice_off,
+                  const uint16_t *__restrict__ perm, const int *__restrict__ slice_off,
                   const T *__restrict__ x, T *__restrict__ y,
-                  int rows, int ncols, int P, int W)
+                  int rows, int ncols, int P, int W, int use_tma)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *xs = reinterpret_cast<T *>(smem_raw);
-
+    using P2 = typename PairT<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    /* layout: [mbarriers 16 B][sums R][xbuf0 W+2][xbuf1 W+2] */
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     const int R = blockDim.x;
+    T *sums = reinterpret_cast<T *>(smem_raw + 16);
+    const size_t xoff = (16 + (size_t)R * sizeof(T) + 15) & ~(size_t)15;
+    const int WS = W + (16 / (int)sizeof(T));            /* buffer stride keeps 16-byte alignment */
+    T *xbuf = reinterpret_cast<T *>(smem_raw + xoff);
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spb = R >> 5;
     const int rb = blockIdx.x;
-    const int row = rb * R + tid;
-    const unsigned lt = lanemask_lt();
-    const bool x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((W * sizeof(T)) % 16 == 0);
+    const int nbuf = P > 1 ? 2 : 1;
 
-    T acc = (T)0;
-    for (int p = 0; p < P; ++p) {
-        const int cbase = p * W;
-        const int cw = min(W, ncols - cbase);
-        __syncthreads();                       /* previous panel fully consumed */
-        if (x_vec_ok) {
-            constexpr int VE = 16 / sizeof(T);
-            const int nv = cw / VE;
-            const int4 *src = reinterpret_cast<const int4 *>(x + cbase);
-            int4 *dst = reinterpret_cast<int4 *>(xs);
-            for (int i = tid; i < nv; i += R) dst[i] = __ldg(src + i);
-            for (int i = nv * VE + tid; i < cw; i += R) xs[i] = __ldg(x + cbase + i);
-        } else {
-            for (int i = tid; i < cw; i += R) xs[i] = __ldg(x + cbase + i);
-        }
-        const size_t tile = (size_t)rb * P + p;
-        const int len = seglen[tile * R + tid];
-        int off = slice_off[tile * spb + warp];
-        __syncthreads();                       /* x slice visible */
-
-        const int maxlen = __reduce_max_sync(0xffffffffu, len);
-        for (int k0 = 0; k0 < maxlen; k0 += U) {
-            int  idx[U];
-            bool act[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                act[u] = (k0 + u) < len;
-                const unsigned m = __ballot_sync(0xffffffffu, act[u]);
-                idx[u] = off + __popc(m & lt);
-                off += __popc(m);
-            }
-            T v[U];
-            int c[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v[u] = (T)0;
-                c[u] = 0;
-                if (act[u]) {
-                    v[u] = __ldcs(val + idx[u]);
-                    c[u] = __ldcs(col + idx[u]);
-                }
-            }
-            T xv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = xs[c[u]];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (act[u]) acc = padd(acc, pmul(v[u], xv[u]));
+    sums[tid] = (T)0;
+    if (tid == 0) {
+        xbuf[W] = (T)0;                                   /* padding slot, never overwritten */
+        if (nbuf == 2) xbuf[WS + W] = (T)0;
+        if (use_tma) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
-    if (row < rows) y[row] = acc;
+    __syncthreads();
+
+    auto issue_panel = [&](int p) {                       /* called by thread 0 only (TMA path) */
+        const int cbase = p * W;
+        const int cw = min(W, ncols - cbase);
+        T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+        constexpr int VE = 16 / sizeof(T);
+        const int cw_al = cw & ~(VE - 1);
+        for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);   /* ragged tail */
+        fence_proxy_async();
+        uint64_t *bar = &bars[p & (nbuf - 1)];
+        if (cw_al > 0) {
+            mbar_expect_tx(bar, (uint32_t)(cw_al * sizeof(T)));
+            /* bulk copies of at most 64 KB each */
+            uint32_t left = (uint32_t)(cw_al * sizeof(T));
+            const char *src = reinterpret_cast<const char *>(x + cbase);
+            char *d = reinterpret_cast<char *>(dst);
+            while (left) {
+                const uint32_t n = left > 65536u ? 65536u : left;
+                tma_bulk_g2s(d, src, n, bar);
+                d += n; src += n; left -= n;
+            }
+        } else {
+            mbar_expect_tx(bar, 0);
+        }
+    };
+    auto coop_panel = [&](int p) {                        /* all threads (fallback path) */
+        const int cbase = p * W;
+        const int cw = min(W, ncols - cbase);
+        T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+        for (int i = tid; i < cw; i += R) dst[i] = __ldg(x + cbase + i);
+    };
+
+    if (use_tma) {
+        if (tid == 0) issue_panel(0);
+    } else {
+        coop_panel(0);
+    }
+
+    for (int p = 0; p < P; ++p) {
+        const size_t tile = (size_t)rb * P + p;
+        const int rr = perm[tile * R + tid];
+        const int off = slice_off[tile * spb + warp];
+        const int npair = (slice_off[tile * spb + warp + 1] - off) >> 6;
+        const P2 *vp = reinterpret_cast<const P2 *>(val) + (size_t)(off >> 1) + lane;
+        const uint32_t *cp = reinterpret_cast<const uint32_t *>(col) + (size_t)(off >> 1) + lane;
+
+        /* first chunk of the matrix stream is requested before waiting for x */
+        Chunk<T, U> a, b;
+        load_chunk<T, U>(a, vp, cp, 0, npair);
+
+        /* buffer (p+1)&1 was released by the barrier that ended panel p-1 */
+        if (use_tma) {
+            if (tid == 0 && p + 1 < P) issue_panel(p + 1);
+            mbar_wait(&bars[p & (nbuf - 1)], (uint32_t)((p >> (nbuf - 1)) & 1));
+        } else {
+            if (p + 1 < P && nbuf == 2) coop_panel(p + 1);
+            __syncthreads();
+        }
+        const T *xs = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+
+        T acc = sums[rr];
+        for (int kp = 0; kp < npair; kp += 2 * U) {
+            load_chunk<T, U>(b, vp, cp, kp + U, npair);
+            acc = consume_chunk<T, U>(a, xs, acc, kp, npair);
+            load_chunk<T, U>(a, vp, cp, kp + 2 * U, npair);
+            acc = consume_chunk<T, U>(b, xs, acc, kp + U, npair);
+        }
+        sums[rr] = acc;
+        __syncthreads();            /* panel p consumed: its x buffer and the sums are free */
+    }
+    const int row = rb * R + tid;
+    if (row < rows) y[row] = sums[tid];
 }
 
 size_t panel_smem_bytes(const DevPanel &pm, bool f32)
 {
-    return (size_t)pm.W * (f32 ? 4 : 8);
+    const size_t es = f32 ? 4 : 8;
+    const size_t xoff = (16 + (size_t)pm.R * es + 15) & ~(size_t)15;
+    const size_t ws = (size_t)pm.W + 16 / es;
+    return xoff + (pm.P > 1 ? 2 : 1) * ws * es;
 }
 
 template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
-    constexpr int U = 8;
+    constexpr int U = 2;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(spmv_panel_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -233,9 +390,10 @@ void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
         attr_set = true;
     }
     const size_t smem = panel_smem_bytes(pm, sizeof(T) == 4);
+    const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panel_kernel<T, U><<<pm.nblk, pm.R, smem, s>>>(
-        static_cast<const T *>(pm.val), pm.col, pm.seglen, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W);
+        static_cast<const T *>(pm.val), pm.col, pm.perm, pm.slice_off, x, y,
+        pm.rows, pm.ncols, pm.P, pm.W, use_tma);
 }
 template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t);
 template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t);

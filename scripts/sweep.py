@@ -30,8 +30,8 @@ for cfg in configs:
     if "x" in cfg and cfg[0].isdigit():
         parts = cfg.split("x")
         env = {"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]}
-        if len(parts) > 2:
-            env["B200_SPMV_PANEL_VARIANT"] = parts[2]
+        if len(parts) > 2 and parts[2] == "notma":
+            env["B200_SPMV_PANEL_TMA"] = "0"
         kernel = "panel"
     os.environ.update(env)
     rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)

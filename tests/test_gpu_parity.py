@@ -128,7 +128,7 @@ def test_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, pa
     a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=True)
     y0 = oracle.spmv(a, x, rowstr, c)
     m, y = _exec_resident(libspmv, a, x, rowstr, c, "auto", panel_env)
-    if len(c) and m.nnz / (m.rows * max(1, -(-m.ncols // int(panel_env.get("B200_SPMV_PANEL_COLS", 16384))))) >= 4:
+    if not panel_env and len(c) and shape["ncols"] <= 20000 and shape["mean"] >= 9:
         assert m.kernel_name == "panel", (m.kernel_name, m.ncols, m.nnz)
     assert np.array_equal(y, y0)
     # the ordered kernel on the same input agrees too
