@@ -92,7 +92,7 @@ struct b200_matrix {
     UploadScan scan;
     /* PANEL layout (when kernel == B200_KERNEL_PANEL) */
     DevPanel panel;
-    void *d_pval; uint16_t *d_pcol; uint16_t *d_perm; int *d_slice_off;
+    void *d_pval; uint16_t *d_pcol; ushort4 *d_meta; int *d_slice_off;
     /* staging owned by the drop-in path (allocated lazily) */
     void *d_x, *d_y;           /* device vectors */
     void *h_x, *h_y;           /* pinned bounce buffers */
@@ -207,14 +207,17 @@ static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<
  * (row, panel) on average. */
 static const size_t kSmemMax = 227 * 1024;
 
-static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out)
+static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out, int *G_out)
 {
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
     const size_t es = elem_size(m->dtype);
+    int G = env_int("B200_SPMV_PANEL_G", 2);
+    G = G == 1 ? 1 : 2;
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) R = (m->rows + g_sm_count - 1) / g_sm_count;
-    R = std::max(32, std::min(1024, (R + 31) & ~31));
+    const int gran = 32 * G;
+    R = std::max(gran, std::min(1024, (R + gran - 1) / gran * gran));
     /* shared memory: 16 B barriers + R sums + nbuf * (W + pad) x entries */
     const size_t fixed = ((16 + (size_t)R * es + 15) & ~(size_t)15) + 64;
     const int w_single = std::min<long long>(65504, (long long)((kSmemMax - fixed) / es) - 4) & ~31;
@@ -231,17 +234,18 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
     }
     const double seg = (double)m->nnz / ((double)m->rows * P);
     if (P > 64 || (seg < 4.0 && P > 1)) return false;
-    *P_out = P; *W_out = W; *R_out = R;
+    *P_out = P; *W_out = W; *R_out = R; *G_out = G;
     return true;
 }
 
 static bool build_panel_locked(b200_matrix *m)
 {
-    int P, W, R;
-    if (!panel_applicable(m, &P, &W, &R)) return false;
+    int P, W, R, G;
+    if (!panel_applicable(m, &P, &W, &R, &G)) return false;
     const size_t es = elem_size(m->dtype);
     const int nblk = (m->rows + R - 1) / R;
-    const int spb = R / 32;
+    const int Tn = R / G;
+    const int spb = Tn / 32;
     const int ntiles = nblk * P;
     const size_t nseg = (size_t)ntiles * R;
     const int nslices = ntiles * spb;
@@ -252,9 +256,9 @@ static bool build_panel_locked(b200_matrix *m)
     CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
     launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
-    CUDA_OK(cudaMalloc((void **)&m->d_perm, nseg * sizeof(uint16_t)));
+    CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)ntiles * Tn * sizeof(ushort4)));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_sort(d_seglen, ntiles, R, m->d_perm, d_cnt, g_stream);
+    launch_panel_sort(d_seglen, ntiles, R, G, m->d_meta, d_cnt, g_stream);
     CUDA_OK(cudaGetLastError());
     int overflow = 0;
     std::vector<int> cnt((size_t)nslices + 1);
@@ -268,8 +272,8 @@ static bool build_panel_locked(b200_matrix *m)
     if (overflow || run > 0x7fffff00LL) {
         CUDA_OK(cudaFree(d_cnt));
         CUDA_OK(cudaFree(d_seglen));
-        CUDA_OK(cudaFree(m->d_perm));
-        m->d_perm = nullptr;
+        CUDA_OK(cudaFree(m->d_meta));
+        m->d_meta = nullptr;
         return false;
     }
     cnt[nslices] = (int)run;
@@ -282,8 +286,9 @@ static bool build_panel_locked(b200_matrix *m)
     CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, g_stream));
     CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
     DevPanel &pm = m->panel;
-    pm.val = m->d_pval; pm.col = m->d_pcol; pm.perm = m->d_perm; pm.slice_off = m->d_slice_off;
-    pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.P = P; pm.W = W; pm.nblk = nblk;
+    pm.val = m->d_pval; pm.col = m->d_pcol; pm.meta = m->d_meta; pm.slice_off = m->d_slice_off;
+    pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.G = G; pm.P = P; pm.W = W; pm.nblk = nblk;
+    pm.U = env_int("B200_SPMV_PANEL_U", 4);
     pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
     pm.padded = run;
     if (m->dtype == B200_F64)
@@ -301,7 +306,7 @@ static bool build_panel_locked(b200_matrix *m)
     CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
     CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
     m->dev.val = nullptr; m->dev.col = nullptr;
-    m->resident_bytes = (int64_t)(nval * es + nval * 2 + nseg * 2 + ((size_t)nslices + 1) * 4 +
+    m->resident_bytes = (int64_t)(nval * es + nval * 2 + (size_t)ntiles * Tn * 8 + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
     return true;
 }
@@ -394,10 +399,10 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d P=%d W=%d padded=%lld]\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d padded=%lld]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m), m->panel.R, m->panel.P, m->panel.W, m->panel.padded);
+                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.padded);
     return m;
 }
 
@@ -405,7 +410,7 @@ static void release_locked(b200_matrix *m)
 {
     if (!m) return;
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
-    cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_perm); cudaFree(m->d_slice_off);
+    cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
     if (m->d_x) cudaFree(m->d_x);
     if (m->d_y) cudaFree(m->d_y);
     if (m->h_x) cudaFreeHost(m->h_x);

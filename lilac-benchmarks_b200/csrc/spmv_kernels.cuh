@@ -59,10 +59,12 @@ int tile_elems(bool f32);
 struct DevPanel {
     const void     *val;        /* T[padded], tile-major SELL-pair order */
     const uint16_t *col;        /* u16[padded], 0-based column inside its panel; W = +0.0 slot */
-    const uint16_t *perm;       /* u16[nblk * P * R]: sorted position -> row inside the block */
+    const ushort4  *meta;       /* [nblk * P * R/G]: {row A, row B, pair where B starts, 0} */
     const int      *slice_off;  /* int[nblk * P * R/32 + 1], element offsets (multiples of 64) */
     int rows, ncols;
-    int R;                      /* rows per row block = threads per CTA (multiple of 32) */
+    int R;                      /* rows per row block (multiple of 32 G) */
+    int G;                      /* rows per thread (1 or 2); the CTA has R/G threads */
+    int U;                      /* pairs per prefetch chunk (tuning) */
     int P;                      /* number of column panels */
     int W;                      /* columns per panel (even) */
     int nblk;                   /* row blocks = CTAs */
@@ -73,7 +75,7 @@ struct DevPanel {
 /* build passes (device side) */
 void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int W, int R,
                         uint16_t *seglen, int *overflow, cudaStream_t s);
-void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, uint16_t *perm,
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, ushort4 *meta,
                        int *slice_elems, cudaStream_t s);
 template <typename T>
 void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows,

@@ -18,14 +18,18 @@
  *
  * Tile layout (built on the device at upload):
  *   inside tile (rb, p) the R rows are sorted by their entry count in panel
- *   p (descending); warp slice w owns sorted positions 32w..32w+31 and is
- *   stored SELL-style in pairs:  element (k, lane) at
- *        slice_off + (k/2)*64 + lane*2 + (k%2)
- *   padded to the slice's longest row rounded up to a pair.  Padding entries
- *   hold value +0.0 and the panel-local column W, a shared-memory slot that
- *   always contains +0.0, so they add +0.0 and change no bit of the sum.
- *   perm[tile][j] maps a sorted position back to its row in the block; the
- *   running sums live in shared memory between panels.
+ *   p (descending).  A CTA has T = R/G threads and every thread ("lane
+ *   stream") owns G rows of the tile: with G = 2, thread t takes sorted ranks
+ *   t and R-1-t (longest with shortest), so all lane streams -- and with them
+ *   all warps -- carry nearly the same number of entries and the per-panel
+ *   barrier costs little.  A lane stream is its rows' entries back to back,
+ *   each row padded to a pair; warp slice w (threads 32w..32w+31) is stored
+ *   SELL-style in pairs:  pair kp of lane l at  slice_off + kp*64 + l*2,
+ *   padded to the slice's longest stream.  Padding entries hold value +0.0
+ *   and the panel-local column W, a shared-memory slot that always contains
+ *   +0.0, so they add +0.0 and change no bit of the sum.  meta[tile][t] =
+ *   {row A, row B, pair index where B starts}; the running sums live in
+ *   shared memory between panels.
  *
  * Data movement: the matrix stream (8 B value + 2 B panel-local column per
  * entry) is read with 128-bit / 32-bit coalesced evict-first loads, software
@@ -125,10 +129,10 @@ void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int 
 /* ---- build: sort the rows of every tile by entry count ------------------- */
 /* one CTA of 1024 threads per tile; bitonic sort of up to 1024 keys
  * (count << 16 | 0xFFFF - row) in descending order => longest first, ties by
- * ascending row. */
+ * ascending row; then the lane streams are formed (G rows per thread). */
 __global__ void __launch_bounds__(1024)
-panel_sort_kernel(const uint16_t *__restrict__ seglen, int R,
-                  uint16_t *__restrict__ perm, int *__restrict__ slice_elems)
+panel_sort_kernel(const uint16_t *__restrict__ seglen, int R, int G,
+                  ushort4 *__restrict__ meta, int *__restrict__ slice_elems)
 {
     __shared__ uint32_t key[1024];
     const int tile = blockIdx.x, t = threadIdx.x;
@@ -145,60 +149,90 @@ panel_sort_kernel(const uint16_t *__restrict__ seglen, int R,
             __syncthreads();
         }
     }
-    if (t < R) {
-        perm[(size_t)tile * R + t] = (uint16_t)(0xFFFF - (key[t] & 0xFFFFu));
-        if ((t & 31) == 0) {
-            const int longest = (int)(key[t] >> 16);
-            slice_elems[tile * (R >> 5) + (t >> 5)] = ((longest + 1) >> 1) * 64;
+    const int T = R / G;
+    int pairs = 0;
+    if (t < T) {
+        const uint32_t ka = key[t];
+        const int la = (int)(ka >> 16);
+        ushort4 mt;
+        mt.x = (unsigned short)(0xFFFF - (ka & 0xFFFFu));
+        mt.y = mt.x;
+        mt.z = 0xFFFF;                       /* never switches */
+        mt.w = 0;
+        pairs = (la + 1) >> 1;
+        if (G == 2) {
+            const uint32_t kb = key[R - 1 - t];
+            const int lb = (int)(kb >> 16);
+            mt.y = (unsigned short)(0xFFFF - (kb & 0xFFFFu));
+            mt.z = (unsigned short)pairs;    /* row B starts at this pair */
+            pairs += (lb + 1) >> 1;
         }
+        meta[(size_t)tile * T + t] = mt;
     }
+    /* all 32 warps take part in the reduction; threads >= T contribute 0 */
+    int mx = pairs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (t < T && (t & 31) == 0) slice_elems[tile * (T >> 5) + (t >> 5)] = mx * 64;
 }
 
-void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, uint16_t *perm,
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, ushort4 *meta,
                        int *slice_elems, cudaStream_t s)
 {
     if (ntiles <= 0) return;
-    panel_sort_kernel<<<ntiles, 1024, 0, s>>>(seglen, R, perm, slice_elems);
+    panel_sort_kernel<<<ntiles, 1024, 0, s>>>(seglen, R, G, meta, slice_elems);
 }
 
 /* ---- build: scatter CSR entries into the padded tile order ---------------- */
 template <typename T>
 __global__ void panel_fill_kernel(const T *__restrict__ val, const int *__restrict__ col,
-                                  const int *__restrict__ rowptr, int rows, int R, int P, int W,
+                                  const int *__restrict__ rowptr, int rows, int R, int G, int P, int W,
                                   const uint16_t *__restrict__ seglen,
-                                  const uint16_t *__restrict__ perm,
+                                  const ushort4 *__restrict__ meta,
                                   const int *__restrict__ slice_off, int nslices,
                                   T *__restrict__ val_out, uint16_t *__restrict__ col_out)
 {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   /* global slice id */
     const int lane = threadIdx.x & 31;
     if (gw >= nslices) return;
-    const int spb = R >> 5;
+    const int Tn = R / G;
+    const int spb = Tn >> 5;
     const int tile = gw / spb, w = gw - tile * spb;
     const int rb = tile / P, p = tile - rb * P;
-    const int rr = perm[(size_t)tile * R + w * 32 + lane];
-    const int r = rb * R + rr;
-    int len = 0, src = 0;
-    if (r < rows) {
-        len = seglen[(size_t)tile * R + rr];
-        src = rowptr[r];
-        for (int q = 0; q < p; ++q) src += seglen[((size_t)rb * P + q) * R + rr];
-    }
+    const ushort4 mt = meta[(size_t)tile * Tn + w * 32 + lane];
     const int off = slice_off[gw];
     const int npair = (slice_off[gw + 1] - off) >> 6;
-    for (int kp = 0; kp < npair; ++kp) {
+    int kp = 0;
+    for (int g = 0; g < G; ++g) {
+        const int rr = g == 0 ? mt.x : mt.y;
+        const int r = rb * R + rr;
+        int len = 0, src = 0;
+        if (r < rows) {
+            len = seglen[(size_t)tile * R + rr];
+            src = rowptr[r];
+            for (int q = 0; q < p; ++q) src += seglen[((size_t)rb * P + q) * R + rr];
+        }
+        for (int k = 0; k < len; k += 2, ++kp) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                T v = (T)0;
+                int c = W;                                 /* the +0.0 slot */
+                if (k + e < len) {
+                    v = val[src + k + e];
+                    c = col[src + k + e] - 1 - p * W;
+                }
+                const size_t idx = (size_t)off + (size_t)kp * 64 + lane * 2 + e;
+                val_out[idx] = v;
+                col_out[idx] = (uint16_t)c;
+            }
+        }
+    }
+    for (; kp < npair; ++kp) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int k = 2 * kp + e;
-            T v = (T)0;
-            int c = W;                                     /* the +0.0 slot */
-            if (k < len) {
-                v = val[src + k];
-                c = col[src + k] - 1 - p * W;
-            }
             const size_t idx = (size_t)off + (size_t)kp * 64 + lane * 2 + e;
-            val_out[idx] = v;
-            col_out[idx] = (uint16_t)c;
+            val_out[idx] = (T)0;
+            col_out[idx] = (uint16_t)W;
         }
     }
 }
@@ -208,11 +242,11 @@ void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows
                        const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
                        cudaStream_t s)
 {
-    const int nslices = pm.nblk * pm.P * (pm.R / 32);
+    const int nslices = pm.nblk * pm.P * (pm.R / pm.G / 32);
     if (nslices <= 0) return;
     const long long threads = (long long)nslices * 32;
     panel_fill_kernel<T><<<(int)((threads + 255) / 256), 256, 0, s>>>(
-        val, col, rowptr, rows, pm.R, pm.P, pm.W, seglen, pm.perm, pm.slice_off, nslices,
+        val, col, rowptr, rows, pm.R, pm.G, pm.P, pm.W, seglen, pm.meta, pm.slice_off, nslices,
         val_out, col_out);
 }
 template void launch_panel_fill<double>(const double *, const int *, const int *, int, const DevPanel &,
@@ -242,8 +276,11 @@ __device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT
     }
 }
 
+/* consume U pairs in order; `sw` is the pair index at which the lane stream
+ * moves on to its second row (running sums parked in shared memory) */
 template <typename T, int U>
-__device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T acc, int kp, int npair)
+__device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T *sums, T acc,
+                                           int kp, int npair, int sw, int &cur, int nxt)
 {
     T xa[U], xb[U];
 #pragma unroll
@@ -256,6 +293,11 @@ __device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (kp + u < npair) {
+            if (kp + u == sw) {
+                sums[cur] = acc;
+                cur = nxt;
+                acc = sums[cur];
+            }
             acc = padd(acc, pmul(ch.v[u].x, xa[u]));
             acc = padd(acc, pmul(ch.v[u].y, xb[u]));
         }
@@ -263,29 +305,29 @@ __device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T
     return acc;
 }
 
-template <typename T, int U>
-__global__ void __launch_bounds__(1024, 1)
+template <typename T, int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
-                  const uint16_t *__restrict__ perm, const int *__restrict__ slice_off,
+                  const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
                   const T *__restrict__ x, T *__restrict__ y,
-                  int rows, int ncols, int P, int W, int use_tma)
+                  int rows, int ncols, int P, int W, int R, int use_tma)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    /* layout: [mbarriers 16 B][sums R][xbuf0 W+2][xbuf1 W+2] */
+    /* layout: [mbarriers 16 B][sums R][xbuf0 W+pad][xbuf1 W+pad] */
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    const int R = blockDim.x;
+    const int Tn = blockDim.x;
     T *sums = reinterpret_cast<T *>(smem_raw + 16);
     const size_t xoff = (16 + (size_t)R * sizeof(T) + 15) & ~(size_t)15;
     const int WS = W + (16 / (int)sizeof(T));            /* buffer stride keeps 16-byte alignment */
     T *xbuf = reinterpret_cast<T *>(smem_raw + xoff);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int spb = R >> 5;
+    const int spb = Tn >> 5;
     const int rb = blockIdx.x;
     const int nbuf = P > 1 ? 2 : 1;
 
-    sums[tid] = (T)0;
+    for (int i = tid; i < R; i += Tn) sums[i] = (T)0;
     if (tid == 0) {
         xbuf[W] = (T)0;                                   /* padding slot, never overwritten */
         if (nbuf == 2) xbuf[WS + W] = (T)0;
@@ -325,7 +367,7 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
-        for (int i = tid; i < cw; i += R) dst[i] = __ldg(x + cbase + i);
+        for (int i = tid; i < cw; i += Tn) dst[i] = __ldg(x + cbase + i);
     };
 
     if (use_tma) {
@@ -336,7 +378,7 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
     for (int p = 0; p < P; ++p) {
         const size_t tile = (size_t)rb * P + p;
-        const int rr = perm[tile * R + tid];
+        const ushort4 mt = meta[tile * Tn + tid];
         const int off = slice_off[tile * spb + warp];
         const int npair = (slice_off[tile * spb + warp + 1] - off) >> 6;
         const P2 *vp = reinterpret_cast<const P2 *>(val) + (size_t)(off >> 1) + lane;
@@ -356,18 +398,22 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         }
         const T *xs = xbuf + (size_t)(p & (nbuf - 1)) * WS;
 
-        T acc = sums[rr];
+        int cur = mt.x;
+        const int nxt = mt.y, sw = mt.z;
+        T acc = sums[cur];
         for (int kp = 0; kp < npair; kp += 2 * U) {
             load_chunk<T, U>(b, vp, cp, kp + U, npair);
-            acc = consume_chunk<T, U>(a, xs, acc, kp, npair);
+            acc = consume_chunk<T, U>(a, xs, sums, acc, kp, npair, sw, cur, nxt);
             load_chunk<T, U>(a, vp, cp, kp + 2 * U, npair);
-            acc = consume_chunk<T, U>(b, xs, acc, kp + U, npair);
+            acc = consume_chunk<T, U>(b, xs, sums, acc, kp + U, npair, sw, cur, nxt);
         }
-        sums[rr] = acc;
+        sums[cur] = acc;
         __syncthreads();            /* panel p consumed: its x buffer and the sums are free */
     }
-    const int row = rb * R + tid;
-    if (row < rows) y[row] = sums[tid];
+    for (int i = tid; i < R; i += Tn) {
+        const int row = rb * R + i;
+        if (row < rows) y[row] = sums[i];
+    }
 }
 
 size_t panel_smem_bytes(const DevPanel &pm, bool f32)
@@ -378,22 +424,34 @@ size_t panel_smem_bytes(const DevPanel &pm, bool f32)
     return xoff + (pm.P > 1 ? 2 : 1) * ws * es;
 }
 
-template <typename T>
-void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+template <typename T, int U, int MAXT>
+static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
-    if (pm.nblk <= 0) return;
-    constexpr int U = 2;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(spmv_panel_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024);
+        cudaFuncSetAttribute(spmv_panel_kernel<T, U, MAXT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     const size_t smem = panel_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
-    spmv_panel_kernel<T, U><<<pm.nblk, pm.R, smem, s>>>(
-        static_cast<const T *>(pm.val), pm.col, pm.perm, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, use_tma);
+    spmv_panel_kernel<T, U, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
+        static_cast<const T *>(pm.val), pm.col, pm.meta, pm.slice_off, x, y,
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma);
+}
+
+template <typename T>
+void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+{
+    if (pm.nblk <= 0) return;
+    const int threads = pm.R / pm.G;
+    if (threads > 512) {
+        launch_panel_cfg<T, 2, 1024>(pm, x, y, s);          /* 64 registers per thread */
+    } else if (pm.U >= 6) {
+        launch_panel_cfg<T, 6, 512>(pm, x, y, s);
+    } else {
+        launch_panel_cfg<T, 4, 512>(pm, x, y, s);           /* 128 registers per thread */
+    }
 }
 template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t);
 template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t);

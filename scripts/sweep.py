@@ -30,8 +30,13 @@ for cfg in configs:
     if "x" in cfg and cfg[0].isdigit():
         parts = cfg.split("x")
         env = {"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]}
-        if len(parts) > 2 and parts[2] == "notma":
-            env["B200_SPMV_PANEL_TMA"] = "0"
+        for opt in parts[2:]:
+            if opt == "notma":
+                env["B200_SPMV_PANEL_TMA"] = "0"
+            elif opt.startswith("g"):
+                env["B200_SPMV_PANEL_G"] = opt[1:]
+            elif opt.startswith("u"):
+                env["B200_SPMV_PANEL_U"] = opt[1:]
         kernel = "panel"
     os.environ.update(env)
     rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
