@@ -217,9 +217,9 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) R = (m->rows + g_sm_count - 1) / g_sm_count;
     const int gran = 32 * G;
-    R = std::max(gran, std::min(1024, (R + gran - 1) / gran * gran));
+    R = std::max(gran, std::min(512 * G, (R + gran - 1) / gran * gran));   /* CTA <= 512 threads */
     /* shared memory: 16 B barriers + R sums + nbuf * (W + pad) x entries */
-    const size_t fixed = ((16 + (size_t)R * es + 15) & ~(size_t)15) + 64;
+    const size_t fixed = ((16 + 64 * 32 * 8 + (size_t)R * es + 15) & ~(size_t)15) + 64;
     const int w_single = std::min<long long>(65504, (long long)((kSmemMax - fixed) / es) - 4) & ~31;
     const int w_double = std::min<long long>(65504, (long long)((kSmemMax - fixed) / (2 * es)) - 4) & ~31;
     int P, W;
@@ -227,7 +227,8 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
         P = 1;
         W = (m->ncols + 31) & ~31;
     } else {
-        int wmax = env_int("B200_SPMV_PANEL_COLS", w_double);
+        /* 96 KB x slices measured best on NPB class C (profiles/r01_run5_sweep.txt) */
+        int wmax = env_int("B200_SPMV_PANEL_COLS", std::min<int>(w_double, (int)(96 * 1024 / es)));
         wmax = std::max(32, std::min(wmax, w_double)) & ~31;
         P = (m->ncols + wmax - 1) / wmax;
         W = (((m->ncols + P - 1) / P) + 31) & ~31;
@@ -288,7 +289,7 @@ static bool build_panel_locked(b200_matrix *m)
     DevPanel &pm = m->panel;
     pm.val = m->d_pval; pm.col = m->d_pcol; pm.meta = m->d_meta; pm.slice_off = m->d_slice_off;
     pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.G = G; pm.P = P; pm.W = W; pm.nblk = nblk;
-    pm.U = env_int("B200_SPMV_PANEL_U", 4);
+    pm.U = env_int("B200_SPMV_PANEL_U", 5);
     pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
     pm.padded = run;
     if (m->dtype == B200_F64)

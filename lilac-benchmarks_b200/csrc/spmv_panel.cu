@@ -305,6 +305,40 @@ __device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T
     return acc;
 }
 
+/* Read cursor over a lane stream: walks the pairs of panel 0, 1, ... of this
+ * warp's slices in chunks of U pairs, so that the matrix stream stays
+ * requested ahead of its use across panel boundaries.  Every panel is walked
+ * in an even number of chunks (consumption alternates two register sets). */
+struct StreamCursor {
+    int p;          /* panel being requested */
+    int kp;         /* next pair inside that panel's slice */
+    int npair;      /* pairs of that slice */
+    int nround;     /* pairs walked for that slice: npair rounded up to 2U */
+    size_t base;    /* pair offset of the slice + lane */
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void cursor_load(Chunk<T, U> &ch, StreamCursor &cur,
+                                            const typename PairT<T>::type *val2,
+                                            const uint32_t *col2, const int2 *s_slice, int spb,
+                                            int warp, int lane, int P)
+{
+    if (cur.p < P) {
+        load_chunk<T, U>(ch, val2 + cur.base, col2 + cur.base, cur.kp, cur.npair);
+        cur.kp += U;
+        if (cur.kp >= cur.nround) {
+            ++cur.p;
+            if (cur.p < P) {
+                const int2 so = s_slice[cur.p * spb + warp];
+                cur.kp = 0;
+                cur.npair = so.y;
+                cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
+                cur.base = (size_t)(so.x >> 1) + lane;
+            }
+        }
+    }
+}
+
 template <typename T, int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
@@ -314,20 +348,29 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    /* layout: [mbarriers 16 B][sums R][xbuf0 W+pad][xbuf1 W+pad] */
+    /* layout: [mbarriers 16 B][slice table P*spb int2][sums R][xbuf0 W+pad][xbuf1 W+pad] */
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     const int Tn = blockDim.x;
-    T *sums = reinterpret_cast<T *>(smem_raw + 16);
-    const size_t xoff = (16 + (size_t)R * sizeof(T) + 15) & ~(size_t)15;
+    const int spb = Tn >> 5;
+    int2 *s_slice = reinterpret_cast<int2 *>(smem_raw + 16);
+    const size_t soff = 16 + (size_t)P * spb * sizeof(int2);
+    T *sums = reinterpret_cast<T *>(smem_raw + soff);
+    const size_t xoff = (soff + (size_t)R * sizeof(T) + 15) & ~(size_t)15;
     const int WS = W + (16 / (int)sizeof(T));            /* buffer stride keeps 16-byte alignment */
     T *xbuf = reinterpret_cast<T *>(smem_raw + xoff);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int spb = Tn >> 5;
     const int rb = blockIdx.x;
     const int nbuf = P > 1 ? 2 : 1;
+    const P2 *val2 = reinterpret_cast<const P2 *>(val);
+    const uint32_t *col2 = reinterpret_cast<const uint32_t *>(col);
 
     for (int i = tid; i < R; i += Tn) sums[i] = (T)0;
+    for (int i = tid; i < P * spb; i += Tn) {
+        const int o = slice_off[(size_t)rb * P * spb + i];
+        const int e = slice_off[(size_t)rb * P * spb + i + 1];
+        s_slice[i] = make_int2(o, (e - o) >> 6);
+    }
     if (tid == 0) {
         xbuf[W] = (T)0;                                   /* padding slot, never overwritten */
         if (nbuf == 2) xbuf[WS + W] = (T)0;
@@ -337,6 +380,7 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
+    ushort4 mt_next = meta[(size_t)rb * P * Tn + tid];
     __syncthreads();
 
     auto issue_panel = [&](int p) {                       /* called by thread 0 only (TMA path) */
@@ -376,17 +420,22 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         coop_panel(0);
     }
 
-    for (int p = 0; p < P; ++p) {
-        const size_t tile = (size_t)rb * P + p;
-        const ushort4 mt = meta[tile * Tn + tid];
-        const int off = slice_off[tile * spb + warp];
-        const int npair = (slice_off[tile * spb + warp + 1] - off) >> 6;
-        const P2 *vp = reinterpret_cast<const P2 *>(val) + (size_t)(off >> 1) + lane;
-        const uint32_t *cp = reinterpret_cast<const uint32_t *>(col) + (size_t)(off >> 1) + lane;
+    /* request the first two chunks of the matrix stream */
+    StreamCursor cur;
+    {
+        const int2 so = s_slice[warp];
+        cur.p = 0; cur.kp = 0; cur.npair = so.y;
+        cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
+        cur.base = (size_t)(so.x >> 1) + lane;
+    }
+    Chunk<T, U> a, b;
+    cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
+    cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);
 
-        /* first chunk of the matrix stream is requested before waiting for x */
-        Chunk<T, U> a, b;
-        load_chunk<T, U>(a, vp, cp, 0, npair);
+    for (int p = 0; p < P; ++p) {
+        const ushort4 mt = mt_next;
+        if (p + 1 < P) mt_next = meta[((size_t)rb * P + p + 1) * Tn + tid];
+        const int npair = s_slice[p * spb + warp].y;
 
         /* buffer (p+1)&1 was released by the barrier that ended panel p-1 */
         if (use_tma) {
@@ -398,16 +447,16 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         }
         const T *xs = xbuf + (size_t)(p & (nbuf - 1)) * WS;
 
-        int cur = mt.x;
-        const int nxt = mt.y, sw = mt.z;
-        T acc = sums[cur];
+        int row_cur = mt.x;
+        const int row_nxt = mt.y, sw = mt.z;
+        T acc = sums[row_cur];
         for (int kp = 0; kp < npair; kp += 2 * U) {
-            load_chunk<T, U>(b, vp, cp, kp + U, npair);
-            acc = consume_chunk<T, U>(a, xs, sums, acc, kp, npair, sw, cur, nxt);
-            load_chunk<T, U>(a, vp, cp, kp + 2 * U, npair);
-            acc = consume_chunk<T, U>(b, xs, sums, acc, kp + U, npair, sw, cur, nxt);
+            acc = consume_chunk<T, U>(a, xs, sums, acc, kp, npair, sw, row_cur, row_nxt);
+            cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
+            acc = consume_chunk<T, U>(b, xs, sums, acc, kp + U, npair, sw, row_cur, row_nxt);
+            cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);
         }
-        sums[cur] = acc;
+        sums[row_cur] = acc;
         __syncthreads();            /* panel p consumed: its x buffer and the sums are free */
     }
     for (int i = tid; i < R; i += Tn) {
@@ -419,7 +468,8 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 size_t panel_smem_bytes(const DevPanel &pm, bool f32)
 {
     const size_t es = f32 ? 4 : 8;
-    const size_t xoff = (16 + (size_t)pm.R * es + 15) & ~(size_t)15;
+    const size_t soff = 16 + (size_t)pm.P * (pm.R / pm.G / 32) * 8;
+    const size_t xoff = (soff + (size_t)pm.R * es + 15) & ~(size_t)15;
     const size_t ws = (size_t)pm.W + 16 / es;
     return xoff + (pm.P > 1 ? 2 : 1) * ws * es;
 }
@@ -444,13 +494,12 @@ template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
-    const int threads = pm.R / pm.G;
-    if (threads > 512) {
-        launch_panel_cfg<T, 2, 1024>(pm, x, y, s);          /* 64 registers per thread */
-    } else if (pm.U >= 6) {
-        launch_panel_cfg<T, 6, 512>(pm, x, y, s);
+    if (pm.U >= 5) {
+        launch_panel_cfg<T, 5, 512>(pm, x, y, s);
+    } else if (pm.U == 3) {
+        launch_panel_cfg<T, 3, 512>(pm, x, y, s);
     } else {
-        launch_panel_cfg<T, 4, 512>(pm, x, y, s);           /* 128 registers per thread */
+        launch_panel_cfg<T, 4, 512>(pm, x, y, s);           /* <= 128 registers per thread */
     }
 }
 template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t);
