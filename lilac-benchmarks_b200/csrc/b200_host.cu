@@ -123,6 +123,7 @@ static std::vector<PinnedRange> g_pinned;
 static uint64_t g_tick = 0;
 static b200_spmv_stats g_stats;
 static int g_validate = 0, g_verbose = 0, g_cache_cap = 4, g_time_kernels = 1;
+static int g_zero_copy = 1, g_auto_pin = 0;
 
 static void dump_stats_at_exit(void)
 {
@@ -154,6 +155,8 @@ static void ensure_init_locked(int device)
     g_verbose = env_int("B200_SPMV_VERBOSE", 0);
     g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
     g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
+    g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
+    g_auto_pin = env_int("B200_SPMV_PIN_HOST", 0);
     memset(&g_stats, 0, sizeof g_stats);
     atexit(dump_stats_at_exit);
     g_ready = true;
@@ -207,7 +210,8 @@ static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<
  * (row, panel) on average. */
 static const size_t kSmemMax = 227 * 1024;
 
-static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out, int *G_out)
+static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out, int *G_out,
+                             int *nbuf_out)
 {
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
@@ -218,31 +222,48 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
     if (R <= 0) R = (m->rows + g_sm_count - 1) / g_sm_count;
     const int gran = 32 * G;
     R = std::max(gran, std::min(512 * G, (R + gran - 1) / gran * gran));   /* CTA <= 512 threads */
-    /* shared memory: 16 B barriers + R sums + nbuf * (W + pad) x entries */
-    const size_t fixed = ((16 + 64 * 32 * 8 + (size_t)R * es + 15) & ~(size_t)15) + 64;
-    const int w_single = std::min<long long>(65504, (long long)((kSmemMax - fixed) / es) - 4) & ~31;
-    const int w_double = std::min<long long>(65504, (long long)((kSmemMax - fixed) / (2 * es)) - 4) & ~31;
-    int P, W;
-    if (m->ncols <= w_single && !getenv("B200_SPMV_PANEL_COLS")) {
-        P = 1;
+    const int spb = R / G / 32;
+    const int kMaxPanels = 128;
+    /* shared memory: 16 B barriers + slice table + R sums + nbuf * (W + pad) x entries */
+    auto width_that_fits = [&](int nbuf, int P) {
+        const size_t fixed = ((16 + (size_t)P * spb * 8 + (size_t)R * es + 15) & ~(size_t)15) + 64;
+        if (fixed >= kSmemMax) return 0;
+        return (int)(std::min<long long>(65504, (long long)((kSmemMax - fixed) / (nbuf * es)) - 4) & ~31);
+    };
+    /* measured on NPB class C (profiles/r01_run5_sweep.txt): 96 KB double-buffered
+     * x slices are the sweet spot; wider single-buffered slices only pay when
+     * the column range is so wide that the double buffer would leave fewer
+     * than ~8 entries per (row, panel). */
+    const int w_one = width_that_fits(1, 1);
+    const int w_pref = std::min<int>(width_that_fits(2, 16), (int)(96 * 1024 / es));
+    int P, W, nbuf;
+    const int force_nbuf = env_int("B200_SPMV_PANEL_NBUF", 0);
+    if (m->ncols <= w_one && !getenv("B200_SPMV_PANEL_COLS")) {
+        P = 1; nbuf = 1;
         W = (m->ncols + 31) & ~31;
     } else {
-        /* 96 KB x slices measured best on NPB class C (profiles/r01_run5_sweep.txt) */
-        int wmax = env_int("B200_SPMV_PANEL_COLS", std::min<int>(w_double, (int)(96 * 1024 / es)));
-        wmax = std::max(32, std::min(wmax, w_double)) & ~31;
+        int wmax = env_int("B200_SPMV_PANEL_COLS", w_pref);
+        nbuf = 2;
+        int Pd = (m->ncols + std::max(32, wmax & ~31) - 1) / std::max(32, wmax & ~31);
+        const double seg_d = (double)m->nnz / ((double)m->rows * Pd);
+        if (force_nbuf == 1 || (force_nbuf == 0 && !getenv("B200_SPMV_PANEL_COLS") && seg_d < 8.0)) {
+            nbuf = 1;
+            wmax = width_that_fits(1, std::min(kMaxPanels, (m->ncols + 16383) / 16384 + 1));
+        }
+        wmax = std::max(32, std::min(wmax, width_that_fits(nbuf, std::min(kMaxPanels, Pd + 1)))) & ~31;
         P = (m->ncols + wmax - 1) / wmax;
         W = (((m->ncols + P - 1) / P) + 31) & ~31;
     }
     const double seg = (double)m->nnz / ((double)m->rows * P);
-    if (P > 64 || (seg < 4.0 && P > 1)) return false;
-    *P_out = P; *W_out = W; *R_out = R; *G_out = G;
+    if (P > kMaxPanels || (seg < 4.0 && P > 1)) return false;
+    *P_out = P; *W_out = W; *R_out = R; *G_out = G; *nbuf_out = nbuf;
     return true;
 }
 
 static bool build_panel_locked(b200_matrix *m)
 {
-    int P, W, R, G;
-    if (!panel_applicable(m, &P, &W, &R, &G)) return false;
+    int P, W, R, G, nbuf;
+    if (!panel_applicable(m, &P, &W, &R, &G, &nbuf)) return false;
     const size_t es = elem_size(m->dtype);
     const int nblk = (m->rows + R - 1) / R;
     const int Tn = R / G;
@@ -291,6 +312,7 @@ static bool build_panel_locked(b200_matrix *m)
     pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.G = G; pm.P = P; pm.W = W; pm.nblk = nblk;
     pm.U = env_int("B200_SPMV_PANEL_U", 5);
     pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
+    pm.nbuf = nbuf;
     pm.padded = run;
     if (m->dtype == B200_F64)
         launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
@@ -400,10 +422,10 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d padded=%lld]\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d nbuf=%d padded=%lld]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.padded);
+                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.padded);
     return m;
 }
 
@@ -533,7 +555,7 @@ static uint64_t fingerprint(const void *a, const int *rowstr, const int *colidx,
     /* sampled FNV-1a over 64 probes of each array: cheap mutation detector */
     uint64_t h = 1469598103934665603ull;
     const int base = rows > 0 ? rowstr[0] - 1 : 0;
-    const int probes = 64;
+    const int probes = 16;
     for (int k = 0; k < probes && nnz > 0; ++k) {
         const int64_t i = base + (nnz - 1) * k / (probes - 1);
         uint64_t v = 0;
@@ -548,15 +570,34 @@ static uint64_t fingerprint(const void *a, const int *rowstr, const int *colidx,
     return h;
 }
 
-static bool host_is_pinned(const void *p, size_t bytes)
+/* Device-usable alias of a pinned (cudaHostAlloc'ed or registered) host range,
+ * or NULL for pageable memory. */
+static void *pinned_device_alias(const void *p, size_t bytes)
 {
-    const char *c = (const char *)p;
-    for (const PinnedRange &r : g_pinned)
-        if (c >= r.lo && c + bytes <= r.hi) return true;
+    (void)bytes;
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return attr.type == cudaMemoryTypeHost;
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (attr.type != cudaMemoryTypeHost) return nullptr;
+    return attr.devicePointer;
+}
+
+/* B200_SPMV_PIN_HOST=1: register a caller vector the first time it is seen, so
+ * later calls move it by direct access instead of the pinned bounce buffer.
+ * Only safe for vectors that outlive the library use (NPB's COMMON arrays,
+ * pagerank's two std::vectors); off by default. */
+static void maybe_auto_pin(const void *p, size_t bytes)
+{
+    if (!g_auto_pin || bytes == 0) return;
+    const char *c = (const char *)p;
+    for (const PinnedRange &r : g_pinned)
+        if (c >= r.lo && c + bytes <= r.hi) return;
+    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        PinnedRange r = {(char *)p, (char *)p + bytes, true};
+        g_pinned.push_back(r);
+    } else {
+        cudaGetLastError();
+    }
 }
 
 static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *colidx,
@@ -618,24 +659,42 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
     b200_matrix *m = lookup_locked(a, rowstr, colidx, n, dtype);
     const double t0 = now_ms();
     if (n > 0) {
-        /* x: host -> device (gpu.c:264) */
+        /* x: host -> device (gpu.c:264).  Pinned caller memory is read straight
+         * over PCIe by a copy kernel on the same stream (no copy-engine hop);
+         * pageable memory goes through the pinned bounce buffer. */
+        maybe_auto_pin(iv, m->x_bytes);
+        maybe_auto_pin(ov, m->y_bytes);
         if (m->ncols > 0) {
-            if (host_is_pinned(iv, m->x_bytes)) {
+            const void *x_alias = pinned_device_alias(iv, m->x_bytes);
+            if (x_alias && g_zero_copy) {
+                launch_copy_in(x_alias, m->d_x, m->x_bytes, g_stream);
+            } else if (x_alias) {
                 CUDA_OK(cudaMemcpyAsync(m->d_x, iv, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
             } else {
                 memcpy(m->h_x, iv, m->x_bytes);
-                CUDA_OK(cudaMemcpyAsync(m->d_x, m->h_x, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
+                if (g_zero_copy) {
+                    void *hx_alias = pinned_device_alias(m->h_x, m->x_bytes);
+                    launch_copy_in(hx_alias, m->d_x, m->x_bytes, g_stream);
+                } else {
+                    CUDA_OK(cudaMemcpyAsync(m->d_x, m->h_x, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
+                }
             }
         }
         if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev0, g_stream));
-        const int launched = exec_locked(m, m->d_x, m->d_y, g_stream);
+        /* y: device -> host (gpu.c:285).  With pinned caller memory the kernel
+         * stores y directly into it; otherwise into the pinned bounce buffer. */
+        void *y_alias = pinned_device_alias(ov, m->y_bytes);
+        const bool y_direct = y_alias != nullptr;
+        void *y_target = nullptr;
+        if (g_zero_copy && m->kernel == B200_KERNEL_PANEL)   /* coalesced y stores only */
+            y_target = y_direct ? y_alias : pinned_device_alias(m->h_y, m->y_bytes);
+        const int launched = exec_locked(m, m->d_x, y_target ? y_target : m->d_y, g_stream);
         if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev1, g_stream));
-        /* y: device -> host (gpu.c:285) */
-        const bool y_pinned = host_is_pinned(ov, m->y_bytes);
-        CUDA_OK(cudaMemcpyAsync(y_pinned ? ov : m->h_y, m->d_y, m->y_bytes,
-                                cudaMemcpyDeviceToHost, g_stream));
+        if (!y_target)
+            CUDA_OK(cudaMemcpyAsync(y_direct ? ov : m->h_y, m->d_y, m->y_bytes,
+                                    cudaMemcpyDeviceToHost, g_stream));
         CUDA_OK(cudaStreamSynchronize(g_stream));
-        if (!y_pinned) memcpy(ov, m->h_y, m->y_bytes);
+        if (!y_direct) memcpy(ov, m->h_y, m->y_bytes);
         if (g_time_kernels) {
             float ms = 0.f;
             CUDA_OK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));

@@ -23,6 +23,8 @@
  */
 #include "spmv_kernels.cuh"
 
+#include <algorithm>
+
 namespace b200 {
 
 /* ---- rounding-exact scalar ops (never contracted into FMA) -------------- */
@@ -280,6 +282,44 @@ void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
     cudaStreamSynchronize(s);           /* `init` is a stack object */
     const int grid = 148 * 8;
     upload_scan_kernel<<<grid, 256, 0, s>>>(rowptr, col, rows, nnz, out);
+}
+
+/* ------------------------------------------------------------------------
+ * x staging: pinned host memory -> device vector, read over PCIe by the SMs
+ * ---------------------------------------------------------------------- */
+__global__ void copy_in_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n16,
+                               const unsigned char *__restrict__ src_tail,
+                               unsigned char *__restrict__ dst_tail, int tail)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+__global__ void copy_in_bytes_kernel(const unsigned char *__restrict__ src,
+                                     unsigned char *__restrict__ dst, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const size_t n16 = bytes / 16;
+        const int tail = (int)(bytes - n16 * 16);
+        const int grid = (int)std::min<size_t>((n16 + 255) / 256 + 1, 148 * 8);
+        copy_in_kernel<<<grid, 256, 0, s>>>(
+            static_cast<const int4 *>(src), static_cast<int4 *>(dst), n16,
+            static_cast<const unsigned char *>(src) + n16 * 16,
+            static_cast<unsigned char *>(dst) + n16 * 16, tail);
+    } else {
+        const int grid = (int)std::min<size_t>((bytes + 255) / 256, 148 * 8);
+        copy_in_bytes_kernel<<<grid, 256, 0, s>>>(static_cast<const unsigned char *>(src),
+                                                  static_cast<unsigned char *>(dst), bytes);
+    }
 }
 
 }  // namespace b200

@@ -52,6 +52,10 @@ void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
 
 int tile_elems(bool f32);
 
+/* dst[0..bytes) = src[0..bytes): src is a device alias of pinned host memory,
+ * so the loads travel over PCIe; runs on the SMs, in stream order */
+void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s);
+
 /* ------------------------------------------------------------------------
  * PANEL: private column-panel layout (built once at upload, on the device);
  * see spmv_panel.cu for the format.
@@ -69,6 +73,7 @@ struct DevPanel {
     int W;                      /* columns per panel (even) */
     int nblk;                   /* row blocks = CTAs */
     int use_tma;                /* x slices by cp.async.bulk (else cooperative loads) */
+    int nbuf;                   /* x slice buffers in shared memory: 2 (prefetch) or 1 (wide) */
     long long padded;           /* stored entries including padding */
 };
 

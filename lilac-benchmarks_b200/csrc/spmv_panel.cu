@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
                   const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
                   const T *__restrict__ x, T *__restrict__ y,
-                  int rows, int ncols, int P, int W, int R, int use_tma)
+                  int rows, int ncols, int P, int W, int R, int use_tma, int nbuf)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,7 +361,6 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = blockIdx.x;
-    const int nbuf = P > 1 ? 2 : 1;
     const P2 *val2 = reinterpret_cast<const P2 *>(val);
     const uint32_t *col2 = reinterpret_cast<const uint32_t *>(col);
 
@@ -437,12 +436,19 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         if (p + 1 < P) mt_next = meta[((size_t)rb * P + p + 1) * Tn + tid];
         const int npair = s_slice[p * spb + warp].y;
 
-        /* buffer (p+1)&1 was released by the barrier that ended panel p-1 */
+        /* double buffer: slot (p+1)&1 was released by the barrier that ended
+         * panel p-1, so panel p+1 is requested while panel p is computed.
+         * single buffer (wide panels): panel p is requested here, after the
+         * barrier that ended panel p-1. */
         if (use_tma) {
-            if (tid == 0 && p + 1 < P) issue_panel(p + 1);
+            if (tid == 0) {
+                if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
+                if (nbuf == 1 && p > 0) issue_panel(p);
+            }
             mbar_wait(&bars[p & (nbuf - 1)], (uint32_t)((p >> (nbuf - 1)) & 1));
         } else {
-            if (p + 1 < P && nbuf == 2) coop_panel(p + 1);
+            if (nbuf == 2 && p + 1 < P) coop_panel(p + 1);
+            if (nbuf == 1 && p > 0) coop_panel(p);
             __syncthreads();
         }
         const T *xs = xbuf + (size_t)(p & (nbuf - 1)) * WS;
@@ -471,7 +477,7 @@ size_t panel_smem_bytes(const DevPanel &pm, bool f32)
     const size_t soff = 16 + (size_t)pm.P * (pm.R / pm.G / 32) * 8;
     const size_t xoff = (soff + (size_t)pm.R * es + 15) & ~(size_t)15;
     const size_t ws = (size_t)pm.W + 16 / es;
-    return xoff + (pm.P > 1 ? 2 : 1) * ws * es;
+    return xoff + (size_t)pm.nbuf * ws * es;
 }
 
 template <typename T, int U, int MAXT>
@@ -487,7 +493,7 @@ static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t 
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panel_kernel<T, U, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const T *>(pm.val), pm.col, pm.meta, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma);
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf);
 }
 
 template <typename T>

@@ -1,0 +1,39 @@
+"""Time the drop-in ABI call (host vectors) on one NPB class; library knobs come from the env.
+usage: [B200_SPMV_ZEROCOPY=0|1] [B200_SPMV_PIN_HOST=1] python scripts/e2e_probe.py C pinned|pageable [iters]"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as entry  # noqa: E402
+
+entry.load_package()
+from lilac_benchmarks_b200 import libspmv, npb  # noqa: E402
+
+cls = sys.argv[1]
+mode = sys.argv[2]
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+m = npb.NpbMatrix(cls)
+rng = np.random.default_rng(0)
+if mode == "pinned":
+    hx = [torch.from_numpy(rng.random(m.n + 2)).pin_memory().numpy() for _ in range(4)]
+    hy = torch.zeros(m.n, dtype=torch.float64).pin_memory().numpy()
+else:
+    hx = [rng.random(m.n + 2) for _ in range(4)]
+    hy = np.zeros(m.n)
+for i in range(8):
+    libspmv.spmv_harness(hy, m.a, hx[i & 3], m.rowstr, m.colidx, m.n)
+libspmv.reset_stats()
+t0 = time.perf_counter()
+for i in range(iters):
+    libspmv.spmv_harness(hy, m.a, hx[i & 3], m.rowstr, m.colidx, m.n)
+dt = (time.perf_counter() - t0) / iters
+st = libspmv.stats()
+import os
+knobs = {k: v for k, v in os.environ.items() if k.startswith("B200_SPMV")}
+print(f"{cls} {mode:9s} {knobs}  e2e {dt * 1e6:8.1f} us/call  kernel {st['kernel_ms'] / iters * 1e3:7.1f} us  "
+      f"lib-internal {st['e2e_ms'] / iters * 1e3:7.1f} us", flush=True)

@@ -18,11 +18,17 @@ from lilac_benchmarks_b200 import libspmv, npb  # noqa: E402
 cls = sys.argv[1] if len(sys.argv) > 1 else "C"
 configs = (sys.argv[2] if len(sys.argv) > 2 else "16384x1024,ordered,vector").split(",")
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-m = npb.NpbMatrix(cls)
+if "/" in cls:                       # "D/8": first 1/8 of the rows of class D (one rank's block)
+    letter, parts = cls.split("/")
+    na = npb.cg_class(letter).na
+    m = npb.NpbMatrix(letter, 0, na // int(parts))
+else:
+    m = npb.NpbMatrix(cls)
+ncols = int(m.colidx.max())
 rng = np.random.default_rng(0)
-xs = [torch.from_numpy(rng.random(m.n + 2)).cuda() for _ in range(4)]
+xs = [torch.from_numpy(rng.random(ncols + 2)).cuda() for _ in range(4)]
 y = torch.zeros(m.n, dtype=torch.float64, device="cuda")
-B = 12 * m.nnz + 4 * (m.n + 1) + 16 * m.n
+B = 12 * m.nnz + 4 * (m.n + 1) + 8 * ncols + 8 * m.n
 y_ref = None
 for cfg in configs:
     env = {}
@@ -37,6 +43,8 @@ for cfg in configs:
                 env["B200_SPMV_PANEL_G"] = opt[1:]
             elif opt.startswith("u"):
                 env["B200_SPMV_PANEL_U"] = opt[1:]
+            elif opt.startswith("b"):
+                env["B200_SPMV_PANEL_NBUF"] = opt[1:]
         kernel = "panel"
     os.environ.update(env)
     rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
