@@ -63,8 +63,11 @@ enum {
     B200_KERNEL_VECTOR  = 2,  /* 2..32 lanes per row + warp-shuffle reduction */
     B200_KERNEL_PANEL   = 3,  /* ORDERED on the column-panel private layout with
                                  x slices staged in shared memory (sorted rows) */
-    B200_KERNEL_MERGE   = 4   /* fixed-nnz split with carry-out fix-up for
+    B200_KERNEL_MERGE   = 4,  /* fixed-nnz split with carry-out fix-up for
                                  heavily skewed row lengths */
+    B200_KERNEL_SELL    = 5   /* lane streams over the sorted-SELL private layout,
+                                 x gathered through L2; left-to-right rows for any
+                                 column order (wide matrices, unsorted rows) */
 };
 
 enum { B200_F64 = 0, B200_F32 = 1 };

@@ -93,6 +93,9 @@ struct b200_matrix {
     /* PANEL layout (when kernel == B200_KERNEL_PANEL) */
     DevPanel panel;
     void *d_pval; uint16_t *d_pcol; ushort4 *d_meta; int *d_slice_off;
+    /* SELL layout (when kernel == B200_KERNEL_SELL) */
+    DevSell sell;
+    int *d_scol; int *d_long_rows;
     /* staging owned by the drop-in path (allocated lazily) */
     void *d_x, *d_y;           /* device vectors */
     void *h_x, *h_y;           /* pinned bounce buffers */
@@ -174,8 +177,9 @@ static int kernel_from_env(int requested)
     if (!strcmp(v, "vector")) return B200_KERNEL_VECTOR;
     if (!strcmp(v, "panel")) return B200_KERNEL_PANEL;
     if (!strcmp(v, "merge")) return B200_KERNEL_MERGE;
+    if (!strcmp(v, "sell")) return B200_KERNEL_SELL;
     if (!strcmp(v, "auto")) return B200_KERNEL_AUTO;
-    die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|merge", v);
+    die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|sell|merge", v);
     return 0;
 }
 
@@ -260,10 +264,17 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
     return true;
 }
 
-static bool build_panel_locked(b200_matrix *m)
+static bool build_panel_locked(b200_matrix *m, bool forced)
 {
     int P, W, R, G, nbuf;
     if (!panel_applicable(m, &P, &W, &R, &G, &nbuf)) return false;
+    {
+        /* every CTA loads the whole x once: only worth it while that stays below the
+         * matrix stream itself (short, wide row blocks fail this: NPB class D shards) */
+        const double x_bytes = (double)((m->rows + R - 1) / R) * (double)P * W * elem_size(m->dtype);
+        const double a_bytes = (double)m->nnz * (elem_size(m->dtype) + 2);
+        if (!forced && x_bytes > a_bytes) return false;
+    }
     const size_t es = elem_size(m->dtype);
     const int nblk = (m->rows + R - 1) / R;
     const int Tn = R / G;
@@ -280,7 +291,7 @@ static bool build_panel_locked(b200_matrix *m)
     launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
     CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)ntiles * Tn * sizeof(ushort4)));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_sort(d_seglen, ntiles, R, G, m->d_meta, d_cnt, g_stream);
+    launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, g_stream);
     CUDA_OK(cudaGetLastError());
     int overflow = 0;
     std::vector<int> cnt((size_t)nslices + 1);
@@ -331,6 +342,98 @@ static bool build_panel_locked(b200_matrix *m)
     m->dev.val = nullptr; m->dev.col = nullptr;
     m->resident_bytes = (int64_t)(nval * es + nval * 2 + (size_t)ntiles * Tn * 8 + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
+    return true;
+}
+/* SELL layout: lane streams with global columns, x gathered through L2.
+ * Applicable to every matrix; rows above the cap go to the long-row kernel. */
+static bool build_sell_locked(b200_matrix *m, const int *rowstr)
+{
+    if (m->rows <= 0 || m->nnz <= 0) return false;
+    const size_t es = elem_size(m->dtype);
+    /* tile geometry measured on NPB class D row blocks, crsmat170 and the
+     * power-law graph (profiles/r01_run11_sweep_sell.txt): 256-row tiles, two
+     * rows per lane (longest with shortest), 2-pair chunks (72 registers, so
+     * 7 CTAs of 128 threads per SM keep the L1TEX gather pipe full). */
+    int G = env_int("B200_SPMV_SELL_G", 2);
+    if (G != 1 && G != 2) G = 2;
+    int R = env_int("B200_SPMV_SELL_ROWS", 128 * G);
+    const int gran = 32 * G;
+    R = std::max(gran, std::min(256 * G, (R + gran - 1) / gran * gran));
+    const double mean = (double)m->nnz / m->rows;
+    int cap = env_int("B200_SPMV_SELL_CAP", 0);
+    if (cap <= 0) cap = (int)std::min(65534.0, std::max(64.0, 4.0 * mean));
+    cap = std::min(cap, 65534);
+    const int nblk = (m->rows + R - 1) / R;
+    const int Tn = R / G, spb = Tn / 32;
+    const int nslices = nblk * spb;
+    /* long rows (host pass over the caller's rowstr) */
+    std::vector<int> long_rows, huge_rows;
+    if (m->scan.max_len > cap)
+        for (int r = 0; r < m->rows; ++r) {
+            const int len = rowstr[r + 1] - rowstr[r];
+            if (len > sell_warp_row_max()) huge_rows.push_back(r);
+            else if (len > cap) long_rows.push_back(r);
+        }
+    const int n_long_warp = (int)long_rows.size();
+    long_rows.insert(long_rows.end(), huge_rows.begin(), huge_rows.end());
+    uint16_t *d_seglen = nullptr;
+    int *d_cnt = nullptr;
+    const size_t nseg = (size_t)nblk * R;
+    CUDA_OK(cudaMalloc((void **)&d_seglen, nseg * sizeof(uint16_t)));
+    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
+    launch_sell_rowlen(m->d_rowptr, m->rows, R, cap, d_seglen, g_stream);
+    CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)nblk * Tn * sizeof(ushort4)));
+    CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
+    launch_panel_sort(d_seglen, nblk, R, G, 1, m->d_meta, d_cnt, g_stream);
+    CUDA_OK(cudaGetLastError());
+    std::vector<int> cnt((size_t)nslices + 1);
+    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    long long run = 0;
+    for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
+    if (run > 0x7fffff00LL) {
+        CUDA_OK(cudaFree(d_cnt)); CUDA_OK(cudaFree(d_seglen)); CUDA_OK(cudaFree(m->d_meta));
+        m->d_meta = nullptr;
+        return false;
+    }
+    cnt[nslices] = (int)run;
+    m->d_slice_off = d_cnt;
+    CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, g_stream));
+    const size_t nval = (size_t)run + 64;
+    CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
+    CUDA_OK(cudaMalloc((void **)&m->d_scol, nval * sizeof(int)));
+    DevSell &sm = m->sell;
+    sm.val = m->d_pval; sm.col = m->d_scol; sm.meta = m->d_meta; sm.slice_off = m->d_slice_off;
+    sm.rows = m->rows; sm.R = R; sm.G = G; sm.nblk = nblk; sm.padded = run;
+    sm.U = env_int("B200_SPMV_SELL_U", 2);
+    sm.n_long = (int)long_rows.size();
+    sm.n_long_warp = n_long_warp;
+    sm.long_rows = nullptr;
+    if (sm.n_long > 0) {
+        CUDA_OK(cudaMalloc((void **)&m->d_long_rows, long_rows.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpyAsync(m->d_long_rows, long_rows.data(), long_rows.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, g_stream));
+        sm.long_rows = m->d_long_rows;
+    }
+    if (m->dtype == B200_F64)
+        launch_sell_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
+                                 d_seglen, (double *)m->d_pval, m->d_scol, g_stream);
+    else
+        launch_sell_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
+                                d_seglen, (float *)m->d_pval, m->d_scol, g_stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaFree(d_seglen));
+    m->resident_bytes = (int64_t)(nval * (es + 4) + (size_t)nblk * Tn * 8 + ((size_t)nslices + 1) * 4 +
+                                  ((size_t)m->rows + 1) * 4);
+    if (sm.n_long == 0) {
+        CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
+        CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
+        m->dev.val = nullptr; m->dev.col = nullptr;
+    } else {
+        m->resident_bytes += (int64_t)(((size_t)m->nnz + kPadElems) * (es + 4));
+    }
     return true;
 }
 
@@ -410,8 +513,11 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     /* kernel choice from the histogram */
     kernel = kernel_from_env(kernel);
     if (kernel == B200_KERNEL_MERGE) kernel = B200_KERNEL_ORDERED;
-    if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL)
-        kernel = build_panel_locked(m) ? B200_KERNEL_PANEL : B200_KERNEL_ORDERED;
+    if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL) {
+        if (build_panel_locked(m, kernel == B200_KERNEL_PANEL)) kernel = B200_KERNEL_PANEL;
+        else kernel = B200_KERNEL_SELL;
+    }
+    if (kernel == B200_KERNEL_SELL && !build_sell_locked(m, rowstr)) kernel = B200_KERNEL_ORDERED;
     m->kernel = kernel;
     {
         const double mean = rows > 0 ? (double)nnz / rows : 0.0;
@@ -422,10 +528,11 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d nbuf=%d padded=%lld]\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d nbuf=%d padded=%lld] sell[R=%d G=%d padded=%lld long=%d/%d]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.padded);
+                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.padded,
+                m->sell.R, m->sell.G, m->sell.padded, m->sell.n_long_warp, m->sell.n_long);
     return m;
 }
 
@@ -434,6 +541,7 @@ static void release_locked(b200_matrix *m)
     if (!m) return;
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
     cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
+    cudaFree(m->d_scol); cudaFree(m->d_long_rows);
     if (m->d_x) cudaFree(m->d_x);
     if (m->d_y) cudaFree(m->d_y);
     if (m->h_x) cudaFreeHost(m->h_x);
@@ -444,11 +552,18 @@ static void release_locked(b200_matrix *m)
 static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s)
 {
     if (m->rows == 0) return 0;
+    int launched_kernels = 1;
     if (m->kernel == B200_KERNEL_PANEL) {
         if (m->dtype == B200_F64)
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else
             launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+    } else if (m->kernel == B200_KERNEL_SELL) {
+        if (m->dtype == B200_F64)
+            launch_sell<double>(m->sell, m->dev, (const double *)d_x, (double *)d_y, s);
+        else
+            launch_sell<float>(m->sell, m->dev, (const float *)d_x, (float *)d_y, s);
+        launched_kernels = 1 + (m->sell.n_long_warp > 0) + (m->sell.n_long > m->sell.n_long_warp);
     } else if (m->dtype == B200_F64) {
         if (m->kernel == B200_KERNEL_VECTOR)
             launch_vector<double>(m->dev, m->lanes, (const double *)d_x, (double *)d_y, s);
@@ -462,7 +577,7 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) die("kernel launch failed: %s", cudaGetErrorString(e));
-    return 1;
+    return launched_kernels;
 }
 
 /* ------------------------------------------------------------------------
@@ -510,10 +625,16 @@ extern "C" const char *b200_spmv_kernel_name(const b200_matrix *m)
     case B200_KERNEL_VECTOR:  return "vector";
     case B200_KERNEL_PANEL:   return "panel";
     case B200_KERNEL_MERGE:   return "merge";
+    case B200_KERNEL_SELL:    return "sell";
     default: return "auto";
     }
 }
-extern "C" int b200_spmv_launches_per_exec(const b200_matrix *m) { return m->rows > 0 ? 1 : 0; }
+extern "C" int b200_spmv_launches_per_exec(const b200_matrix *m)
+{
+    if (m->rows <= 0) return 0;
+    return m->kernel == B200_KERNEL_SELL
+               ? 1 + (m->sell.n_long_warp > 0) + (m->sell.n_long > m->sell.n_long_warp) : 1;
+}
 extern "C" int64_t b200_spmv_algorithmic_bytes(const b200_matrix *m)
 {
     const int64_t es = (int64_t)elem_size(m->dtype);

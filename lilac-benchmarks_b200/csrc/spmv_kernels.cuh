@@ -80,7 +80,7 @@ struct DevPanel {
 /* build passes (device side) */
 void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int W, int R,
                         uint16_t *seglen, int *overflow, cudaStream_t s);
-void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, ushort4 *meta,
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, int mode, ushort4 *meta,
                        int *slice_elems, cudaStream_t s);
 template <typename T>
 void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows,
@@ -90,5 +90,30 @@ void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows
 template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
 size_t panel_smem_bytes(const DevPanel &pm, bool f32);
+
+/* ------------------------------------------------------------------------
+ * SELL: the same lane-stream layout without column panels -- x is gathered
+ * through L2 with full 32-bit column indices.  Order-preserving for every
+ * row up to `cap` entries, any column order; see spmv_sell.cu.
+ * ---------------------------------------------------------------------- */
+struct DevSell {
+    const void    *val;        /* T[padded], SELL-pair order */
+    const int     *col;        /* int[padded], 1-based global column (padding: 1) */
+    const ushort4 *meta;       /* [nblk * R/G]: {row A, row B, entries of A, entries of B} */
+    const int     *slice_off;  /* int[nblk * R/G/32 + 1] element offsets (multiples of 64) */
+    int rows, R, G, nblk, U;
+    long long padded;
+    /* rows longer than the cap are left to a CTA-wide (re-ordering) reduction */
+    const int *long_rows;      /* device list of row ids: warp tier first, then CTA tier */
+    int n_long;
+    int n_long_warp;
+};
+void launch_sell_rowlen(const int *rowptr, int rows, int R, int cap, uint16_t *seglen, cudaStream_t s);
+template <typename T>
+void launch_sell_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm,
+                      const uint16_t *seglen, T *val_out, int *col_out, cudaStream_t s);
+int sell_warp_row_max();
+template <typename T>
+void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStream_t s);
 
 }  // namespace b200

@@ -131,7 +131,7 @@ void launch_panel_count(const int *rowptr, const int *col, int rows, int P, int 
  * (count << 16 | 0xFFFF - row) in descending order => longest first, ties by
  * ascending row; then the lane streams are formed (G rows per thread). */
 __global__ void __launch_bounds__(1024)
-panel_sort_kernel(const uint16_t *__restrict__ seglen, int R, int G,
+panel_sort_kernel(const uint16_t *__restrict__ seglen, int R, int G, int mode,
                   ushort4 *__restrict__ meta, int *__restrict__ slice_elems)
 {
     __shared__ uint32_t key[1024];
@@ -166,7 +166,9 @@ panel_sort_kernel(const uint16_t *__restrict__ seglen, int R, int G,
             mt.y = (unsigned short)(0xFFFF - (kb & 0xFFFFu));
             mt.z = (unsigned short)pairs;    /* row B starts at this pair */
             pairs += (lb + 1) >> 1;
+            if (mode == 1) mt.w = (unsigned short)lb;
         }
+        if (mode == 1) mt.z = (unsigned short)la;   /* SELL family: entry counts of A and B */
         meta[(size_t)tile * T + t] = mt;
     }
     /* all 32 warps take part in the reduction; threads >= T contribute 0 */
@@ -176,11 +178,11 @@ panel_sort_kernel(const uint16_t *__restrict__ seglen, int R, int G,
     if (t < T && (t & 31) == 0) slice_elems[tile * (T >> 5) + (t >> 5)] = mx * 64;
 }
 
-void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, ushort4 *meta,
+void launch_panel_sort(const uint16_t *seglen, int ntiles, int R, int G, int mode, ushort4 *meta,
                        int *slice_elems, cudaStream_t s)
 {
     if (ntiles <= 0) return;
-    panel_sort_kernel<<<ntiles, 1024, 0, s>>>(seglen, R, G, meta, slice_elems);
+    panel_sort_kernel<<<ntiles, 1024, 0, s>>>(seglen, R, G, mode, meta, slice_elems);
 }
 
 /* ---- build: scatter CSR entries into the padded tile order ---------------- */

@@ -1,0 +1,301 @@
+/*
+ * spmv_sell.cu -- the SELL kernel family: order-preserving CSR SpMV for
+ * matrices whose column range is too wide for shared-memory x slices
+ * (NPB class D row blocks, SparseBench crsmat, graphs).  x is gathered
+ * through the read-only path and lives in B200's 126 MB L2.
+ *
+ * Layout (built on the device at upload, same lane-stream idea as the PANEL
+ * family, spmv_panel.cu): rows are cut into tiles of R rows; inside a tile
+ * they are sorted by length and dealt to the T = R/G threads longest with
+ * shortest, so all lanes of a warp -- and all warps -- carry about the same
+ * number of entries.  A lane stream is row A's entries, padded to a pair,
+ * followed by row B's; warp slices are stored SELL-style in pairs
+ * (pair kp of lane l at slice_off + kp*64 + l*2) with 32-bit global columns.
+ * Every lane walks its rows left to right with a separately rounded multiply
+ * and a separately rounded add: bit-identical to libspmv/native-impl.c:1-12
+ * whatever the column order (unsorted and repeated columns included).
+ *
+ * Rows longer than the cap (65534 entries, or far above the mean) would
+ * serialise one lane; they are excluded from the tiles and reduced by a whole
+ * CTA each (tree order) from the CSR copy.
+ *
+ * Roofline: HBM stream 12 B per entry; the binding resource on B200 is the
+ * L1TEX wavefront rate of the divergent x gather (one wavefront per entry per
+ * SM clock), i.e. about half the HBM roofline for fp64.
+ */
+#include "spmv_kernels.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ double smul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  smul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float  sadd(float a, float b)   { return __fadd_rn(a, b); }
+
+template <typename T> struct SPair;
+template <> struct SPair<double> { using type = double2; };
+template <> struct SPair<float>  { using type = float2; };
+
+/* ---- build: row lengths per tile (rows above the cap are left out) -------- */
+__global__ void sell_rowlen_kernel(const int *__restrict__ rowptr, int rows, int cap,
+                                   uint16_t *__restrict__ seglen)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int len = rowptr[r + 1] - rowptr[r];
+    seglen[r] = (uint16_t)(len <= cap ? len : 0);
+}
+
+void launch_sell_rowlen(const int *rowptr, int rows, int R, int cap, uint16_t *seglen, cudaStream_t s)
+{
+    (void)R;   /* tiles are consecutive runs of R rows: seglen[tile * R + rr] == seglen[row] */
+    if (rows <= 0) return;
+    sell_rowlen_kernel<<<(rows + 255) / 256, 256, 0, s>>>(rowptr, rows, cap, seglen);
+}
+
+/* ---- build: scatter CSR entries into the lane streams ---------------------- */
+template <typename T>
+__global__ void sell_fill_kernel(const T *__restrict__ val, const int *__restrict__ col,
+                                 const int *__restrict__ rowptr, int rows, int R, int G,
+                                 const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
+                                 int nslices, T *__restrict__ val_out, int *__restrict__ col_out)
+{
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= nslices) return;
+    const int Tn = R / G;
+    const int spb = Tn >> 5;
+    const int tile = gw / spb, w = gw - tile * spb;
+    const ushort4 mt = meta[(size_t)tile * Tn + w * 32 + lane];
+    const int off = slice_off[gw];
+    const int npair = (slice_off[gw + 1] - off) >> 6;
+    int kp = 0;
+    for (int g = 0; g < G; ++g) {
+        const int r = tile * R + (g == 0 ? mt.x : mt.y);
+        const int len = g == 0 ? mt.z : mt.w;
+        const int src = r < rows ? rowptr[r] : 0;
+        for (int k = 0; k < len; k += 2, ++kp) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                T v = (T)0;
+                int c = 1;
+                if (k + e < len) {
+                    v = val[src + k + e];
+                    c = col[src + k + e];
+                }
+                const size_t idx = (size_t)off + (size_t)kp * 64 + lane * 2 + e;
+                val_out[idx] = v;
+                col_out[idx] = c;
+            }
+        }
+    }
+    for (; kp < npair; ++kp) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const size_t idx = (size_t)off + (size_t)kp * 64 + lane * 2 + e;
+            val_out[idx] = (T)0;
+            col_out[idx] = 1;
+        }
+    }
+}
+
+template <typename T>
+void launch_sell_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm,
+                      const uint16_t *seglen, T *val_out, int *col_out, cudaStream_t s)
+{
+    (void)seglen;
+    const int nslices = sm.nblk * (sm.R / sm.G / 32);
+    if (nslices <= 0) return;
+    const long long threads = (long long)nslices * 32;
+    sell_fill_kernel<T><<<(int)((threads + 255) / 256), 256, 0, s>>>(
+        val, col, rowptr, rows, sm.R, sm.G, sm.meta, sm.slice_off, nslices, val_out, col_out);
+}
+template void launch_sell_fill<double>(const double *, const int *, const int *, int, const DevSell &,
+                                       const uint16_t *, double *, int *, cudaStream_t);
+template void launch_sell_fill<float>(const float *, const int *, const int *, int, const DevSell &,
+                                      const uint16_t *, float *, int *, cudaStream_t);
+
+/* ------------------------------------------------------------------------
+ * the product
+ * ---------------------------------------------------------------------- */
+template <typename T, int U>
+struct SChunk {
+    typename SPair<T>::type v[U];
+    int2 c[U];
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void sell_load(SChunk<T, U> &ch, const typename SPair<T>::type *vp,
+                                          const int2 *cp, int kp, int npair)
+{
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            ch.v[u] = __ldcs(vp + (size_t)(kp + u) * 32);
+            ch.c[u] = __ldcs(cp + (size_t)(kp + u) * 32);
+        }
+    }
+}
+
+/* entries [0, lenA) belong to row A, [swE, endE) to row B (swE = lenA rounded
+ * up to a pair); everything else in the slice is padding and is skipped */
+template <typename T, int U>
+__device__ __forceinline__ T sell_consume(const SChunk<T, U> &ch, const T *__restrict__ xm1,
+                                          T *y, T acc, int kp, int npair,
+                                          int lenA, int swE, int endE, int rowA, int rowB, int rows)
+{
+    T xa[U], xb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            xa[u] = __ldg(xm1 + ch.c[u].x);
+            xb[u] = __ldg(xm1 + ch.c[u].y);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            const int e0 = 2 * (kp + u);
+            if (e0 == swE && swE < endE) {         /* row A complete, row B starts */
+                if (rowA < rows) y[rowA] = acc;
+                acc = (T)0;
+            }
+            if (e0 < lenA || (e0 >= swE && e0 < endE)) acc = sadd(acc, smul(ch.v[u].x, xa[u]));
+            if (e0 + 1 < lenA || (e0 + 1 >= swE && e0 + 1 < endE)) acc = sadd(acc, smul(ch.v[u].y, xb[u]));
+        }
+    }
+    (void)rowB;
+    return acc;
+}
+
+template <typename T, int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+spmv_sell_kernel(const T *__restrict__ val, const int *__restrict__ col,
+                 const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
+                 const T *__restrict__ xm1, T *__restrict__ y, int rows, int R, int G)
+{
+    using P2 = typename SPair<T>::type;
+    const int Tn = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int spb = Tn >> 5;
+    const int tile = blockIdx.x;
+    const ushort4 mt = meta[(size_t)tile * Tn + tid];
+    const int off = slice_off[tile * spb + warp];
+    const int npair = (slice_off[tile * spb + warp + 1] - off) >> 6;
+    const P2 *vp = reinterpret_cast<const P2 *>(val) + (size_t)(off >> 1) + lane;
+    const int2 *cp = reinterpret_cast<const int2 *>(col) + (size_t)(off >> 1) + lane;
+
+    /* the tile's y is assembled in shared memory and stored coalesced */
+    extern __shared__ __align__(16) unsigned char sell_smem[];
+    T *ytile = reinterpret_cast<T *>(sell_smem);
+    T *yout = y;
+    y = ytile;
+    const int rows_g = rows;
+    rows = R;                                   /* bounds for the staged stores: inside the tile */
+    const int rowA = mt.x, rowB = mt.y;
+    const int lenA = mt.z;
+    const int swE = G == 2 ? (lenA + 1) & ~1 : 0x7fffffff;
+    const int endE = G == 2 ? swE + mt.w : lenA;
+
+    SChunk<T, U> a, b;
+    sell_load<T, U>(a, vp, cp, 0, npair);
+    sell_load<T, U>(b, vp, cp, U, npair);
+    T acc = (T)0;
+    for (int kp = 0; kp < npair; kp += 2 * U) {
+        acc = sell_consume<T, U>(a, xm1, y, acc, kp, npair, lenA, swE, endE, rowA, rowB, rows);
+        sell_load<T, U>(a, vp, cp, kp + 2 * U, npair);
+        acc = sell_consume<T, U>(b, xm1, y, acc, kp + U, npair, lenA, swE, endE, rowA, rowB, rows);
+        sell_load<T, U>(b, vp, cp, kp + 3 * U, npair);
+    }
+    /* which row does the running sum belong to?  B if it was entered */
+    if (G == 2 && swE < endE) {             /* A was stored at the switch */
+        if (rowB < rows) y[rowB] = acc;
+    } else {
+        if (rowA < rows) y[rowA] = acc;
+        if (G == 2 && rowB < rows && rowB != rowA) y[rowB] = (T)0;   /* B has no entries */
+    }
+    __syncthreads();
+    for (int i = tid; i < R; i += Tn) {
+        const int r = tile * R + i;
+        if (r < rows_g) yout[r] = ytile[i];
+    }
+}
+
+/* long rows, tier 1: one warp per row (cap < len <= kWarpRowMax), tier 2: one
+ * CTA per row.  Tree-ordered reductions over the CSR copy. */
+constexpr int kWarpRowMax = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmv_long_rows_warp_kernel(const T *__restrict__ val, const int *__restrict__ col,
+                           const int *__restrict__ rowptr, const int *__restrict__ long_rows,
+                           int n_long, const T *__restrict__ xm1, T *__restrict__ y)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_long) return;
+    const int r = long_rows[w];
+    const int lo = rowptr[r], hi = rowptr[r + 1];
+    T acc = (T)0;
+    for (int i = lo + lane; i < hi; i += 32)
+        acc = sadd(acc, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (lane == 0) y[r] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmv_long_rows_kernel(const T *__restrict__ val, const int *__restrict__ col,
+                      const int *__restrict__ rowptr, const int *__restrict__ long_rows,
+                      const T *__restrict__ xm1, T *__restrict__ y)
+{
+    __shared__ T red[8];
+    const int r = long_rows[blockIdx.x];
+    const int lo = rowptr[r], hi = rowptr[r + 1];
+    T acc = (T)0;
+    for (int i = lo + threadIdx.x; i < hi; i += 256)
+        acc = sadd(acc, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T s = (T)0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s = sadd(s, red[w]);
+        y[r] = s;
+    }
+}
+
+int sell_warp_row_max() { return kWarpRowMax; }
+
+template <typename T, int U>
+static void launch_sell_u(const DevSell &sm, const T *x, T *y, cudaStream_t s)
+{
+    spmv_sell_kernel<T, U, 256><<<sm.nblk, sm.R / sm.G, (size_t)sm.R * sizeof(T), s>>>(
+        static_cast<const T *>(sm.val), sm.col, sm.meta, sm.slice_off, x - 1, y, sm.rows, sm.R, sm.G);
+}
+
+template <typename T>
+void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStream_t s)
+{
+    if (sm.nblk > 0) {
+        if (sm.U >= 6) launch_sell_u<T, 6>(sm, x, y, s);
+        else if (sm.U <= 2) launch_sell_u<T, 2>(sm, x, y, s);
+        else launch_sell_u<T, 4>(sm, x, y, s);
+    }
+    /* long_rows = [n_long_warp rows for the warp tier][the rest for the CTA tier] */
+    if (sm.n_long_warp > 0)
+        spmv_long_rows_warp_kernel<T><<<(sm.n_long_warp + 7) / 8, 256, 0, s>>>(
+            static_cast<const T *>(csr.val), csr.col, csr.rowptr, sm.long_rows, sm.n_long_warp,
+            x - 1, y);
+    if (sm.n_long > sm.n_long_warp)
+        spmv_long_rows_kernel<T><<<sm.n_long - sm.n_long_warp, 256, 0, s>>>(
+            static_cast<const T *>(csr.val), csr.col, csr.rowptr, sm.long_rows + sm.n_long_warp,
+            x - 1, y);
+}
+template void launch_sell<double>(const DevSell &, const DevCsr &, const double *, double *, cudaStream_t);
+template void launch_sell<float>(const DevSell &, const DevCsr &, const float *, float *, cudaStream_t);
+
+}  // namespace b200

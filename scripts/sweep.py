@@ -18,7 +18,24 @@ from lilac_benchmarks_b200 import libspmv, npb  # noqa: E402
 cls = sys.argv[1] if len(sys.argv) > 1 else "C"
 configs = (sys.argv[2] if len(sys.argv) > 2 else "16384x1024,ordered,vector").split(",")
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-if "/" in cls:                       # "D/8": first 1/8 of the rows of class D (one rank's block)
+if cls.startswith("crsmat"):
+    from lilac_benchmarks_b200 import gen
+
+    class _M:
+        pass
+    m = _M()
+    m.a, m.colidx, m.rowstr, m.n = gen.crsmat(int(cls[6:]))
+    m.nnz = len(m.a)
+elif cls.startswith("pl"):
+    from lilac_benchmarks_b200 import gen
+
+    class _M:
+        pass
+    m = _M()
+    m.a, m.colidx, m.rowstr, _x0 = gen.powerlaw_graph(1 << int(cls[2:]))
+    m.n = len(m.rowstr) - 1
+    m.nnz = len(m.a)
+elif "/" in cls:                       # "D/8": first 1/8 of the rows of class D (one rank's block)
     letter, parts = cls.split("/")
     na = npb.cg_class(letter).na
     m = npb.NpbMatrix(letter, 0, na // int(parts))
@@ -33,7 +50,12 @@ y_ref = None
 for cfg in configs:
     env = {}
     kernel = cfg
-    if "x" in cfg and cfg[0].isdigit():
+    if cfg.startswith("sell:"):
+        kernel = "sell"
+        for kv in cfg[5:].split(";"):
+            k, v = kv.split("=")
+            env["B200_SPMV_SELL_" + {"R": "ROWS", "G": "G", "U": "U", "C": "CAP"}[k]] = v
+    elif "x" in cfg and cfg[0].isdigit():
         parts = cfg.split("x")
         env = {"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]}
         for opt in parts[2:]:

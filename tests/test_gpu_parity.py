@@ -140,8 +140,46 @@ def test_panel_falls_back_when_rows_are_unsorted(libspmv, oracle):
     rng = np.random.default_rng(77)
     a, c, rowstr, x = make_csr(rng, 2000, 3000, rng.poisson(40, 2000), sort=False)
     m, y = _exec_resident(libspmv, a, x, rowstr, c, "panel")
-    assert m.kernel_name == "ordered"
+    assert m.kernel_name == "sell"
     assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("sort", [True, False])
+@pytest.mark.parametrize("shape", [
+    dict(n=1, ncols=1, mean=1), dict(n=65, ncols=9, mean=3), dict(n=5000, ncols=300000, mean=5),
+    dict(n=3000, ncols=1500000, mean=120), dict(n=777, ncols=50000, mean=400),
+])
+@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SELL_G": 1, "B200_SPMV_SELL_ROWS": 64},
+                                 {"B200_SPMV_SELL_U": 2}, {"B200_SPMV_SELL_U": 6}])
+def test_sell_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape, env):
+    """Lane streams over L2 gathers: left-to-right rows whatever the column
+    order, for every row up to the cap."""
+    rng = np.random.default_rng(shape["n"] + shape["mean"] + int(sort))
+    lens = rng.poisson(shape["mean"], shape["n"])
+    lens[rng.random(shape["n"]) < 0.1] = 0
+    a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=sort)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "sell", env)
+    assert m.kernel_name == "sell" or m.nnz == 0
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+
+
+def test_sell_long_rows_go_to_the_cta_reduction(libspmv, oracle):
+    """Rows above the cap are tree-reduced (re-ordered): exact on the short
+    rows, within 1e-12 relative on the long ones for non-cancelling input."""
+    rng = np.random.default_rng(123)
+    n = 4000
+    lens = rng.poisson(6, n)
+    long_ids = rng.choice(n, 25, replace=False)
+    lens[long_ids] = rng.integers(300, 70000, 25)
+    a, c, rowstr, x = make_csr(rng, n, 200000, lens, positive=True, sort=False)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "auto")
+    assert m.kernel_name == "sell" and m.launches_per_exec == 3
+    y0 = oracle.spmv(a, x, rowstr, c)
+    is_long = np.zeros(n, dtype=bool)
+    is_long[long_ids] = True
+    assert np.array_equal(y[~is_long], y0[~is_long])
+    assert np.all(np.abs(y - y0)[is_long] <= REL_TOL_F64 * np.abs(y0)[is_long])
 
 
 def test_ragged_edges(libspmv, oracle):
