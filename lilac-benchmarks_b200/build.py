@@ -43,7 +43,12 @@ def build_callers(quiet=True):
 
 
 def build_oracle(quiet=True):
-    return _make(ORACLE, "all", quiet=quiet)
+    out = _make(ORACLE, "all", quiet=quiet)
+    # when the reference tree is here, also relink its own C/C++ callers
+    # (parboil spmv cpu, bfs), unchanged, against the b200 platform
+    if Path("/root/reference/libspmv/native.c").exists() and B200_SO.exists():
+        out += _make(ORACLE, "relink", f"B200_SO={B200_SO}", quiet=quiet)
+    return out
 
 
 def build_all(quiet=True):

@@ -53,6 +53,20 @@ def native_vectors():
 
 
 @pytest.fixture(scope="session")
+def parboil():
+    z = np.load(GOLDEN / "parboil_spmv.npz")
+    return {n: {f: z[f"{n}.{f}"] for f in ("a", "colidx", "rowstr", "x", "y_golden")}
+            for n in ("small", "medium")}
+
+
+def parboil_compare(ref, got):
+    """parboil/benchmarks/spmv/tools/compare-output:12-37: abs tol 1e-4 * max|ref| OR rel 0.2 %."""
+    abstol = 1e-4 * np.abs(ref).max()
+    diff = np.abs(ref.astype(np.float64) - got.astype(np.float64))
+    return bool(np.all((diff <= abstol) | (diff < 0.002 * np.abs(ref))))
+
+
+@pytest.fixture(scope="session")
 def npb_history():
     return json.loads((GOLDEN / "npb_history.json").read_text())
 

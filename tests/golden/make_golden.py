@@ -14,6 +14,12 @@ Run in the build container (needs /root/reference and `make -C oracle all`):
                            classes S, W, A, plus the zeta constants of
                            NPB3.3.1/CG/cg.f:122-166.
   libspmv_test_kat.json    the known-answer vector of libspmv/test.cpp:44-49.
+  parboil_spmv.npz         the fp32 CSR + x that parboil's CPU caller feeds
+                           f_spmv_harness_ for its small / medium datasets,
+                           recorded from the reference program, with the
+                           reference's golden outputs; plus the small .mtx,
+                           vector.bin, .out and bfs/input.mtx as data files for
+                           the relinked-binary tests.
 """
 import json
 import os
@@ -122,7 +128,60 @@ def make_kat():
     print("wrote libspmv_test_kat.json")
 
 
+def read_record(path):
+    """File written by oracle/record_harness.c."""
+    raw = open(path, "rb").read()
+    hdr = np.frombuffer(raw, dtype=np.int64, count=5)
+    assert hdr[0] == 0x53504D56
+    f32, rows, nnz, ncols = bool(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[4])
+    off = 40
+    rowstr = np.frombuffer(raw, dtype=np.int32, count=rows + 1, offset=off); off += 4 * (rows + 1)
+    colidx = np.frombuffer(raw, dtype=np.int32, count=nnz, offset=off); off += 4 * nnz
+    dt = np.float32 if f32 else np.float64
+    a = np.frombuffer(raw, dtype=dt, count=nnz, offset=off); off += a.itemsize * nnz
+    x = np.frombuffer(raw, dtype=dt, count=ncols, offset=off)
+    return a.copy(), colidx.copy(), rowstr.copy(), x.copy()
+
+
+def make_parboil():
+    """The fp32 caller: run the reference's parboil spmv CPU program (built into
+    oracle/_ref by oracle/Makefile) against a recording backend to capture the
+    exact CSR it feeds f_spmv_harness_ (main.c:80-95), and keep the reference's
+    golden outputs (datasets/spmv/*/output/*.out) beside it.  The small
+    MatrixMarket input itself is copied so the relinked binary can run on the
+    GPU box."""
+    import shutil
+    import tempfile
+    ds = Path("/root/reference/parboil/datasets/spmv")
+    out = {}
+    for name, mtx in (("small", "1138_bus.mtx"), ("medium", "bcsstk18.mtx")):
+        with tempfile.TemporaryDirectory() as td:
+            rec = os.path.join(td, "rec.bin")
+            env = dict(os.environ, SPMV_RECORD_PATH=rec)
+            subprocess.run([str(ROOT / "oracle" / "_ref" / "parboil_spmv.record"), "-i",
+                            f"{ds / name / 'input' / mtx},{ds / name / 'input' / 'vector.bin'}",
+                            "-o", os.path.join(td, "y.out")], env=env, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            a, c, rowstr, x = read_record(rec)
+        gold = np.fromfile(ds / name / "output" / f"{mtx}.out", dtype=np.uint8)
+        n = int(np.frombuffer(gold[:4].tobytes(), dtype=np.uint32)[0])
+        y = np.frombuffer(gold[4:].tobytes(), dtype=np.float32, count=n)
+        assert n == len(rowstr) - 1
+        for k, v in (("a", a), ("colidx", c), ("rowstr", rowstr), ("x", x), ("y_golden", y)):
+            out[f"{name}.{k}"] = v
+    np.savez_compressed(HERE / "parboil_spmv.npz", **out)
+    shutil.copy(ds / "small" / "input" / "1138_bus.mtx", HERE / "parboil_small_1138_bus.mtx")
+    shutil.copy(ds / "small" / "input" / "vector.bin", HERE / "parboil_small_vector.bin")
+    shutil.copy(ds / "small" / "output" / "1138_bus.mtx.out", HERE / "parboil_small_1138_bus.mtx.out")
+    shutil.copy("/root/reference/bfs/input.mtx", HERE / "bfs_input.mtx")
+    for f in ("parboil_small_1138_bus.mtx", "parboil_small_vector.bin",
+              "parboil_small_1138_bus.mtx.out", "bfs_input.mtx"):
+        os.chmod(HERE / f, 0o644)
+    print("wrote parboil_spmv.npz (+ small inputs, bfs input)")
+
+
 if __name__ == "__main__":
     make_kat()
     make_native_vectors()
     make_npb_history()
+    make_parboil()

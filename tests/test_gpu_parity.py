@@ -307,3 +307,42 @@ def test_class_c_full_size_properties(libspmv, oracle, npb):
     y1 = dy.cpu().numpy().copy()
     rm.exec(torch.from_numpy(4.0 * x).cuda(), dy)
     assert np.array_equal(dy.cpu().numpy(), 4.0 * y1)
+
+
+def test_parboil_fp32_golden(libspmv, oracle, parboil):
+    """f_spmv_harness_ on the exact CSR parboil's CPU caller builds
+    (parboil/benchmarks/spmv/src/cpu/main.c:80-95): bit-identical to the fp32
+    oracle, and inside the reference checker's tolerance of the golden files."""
+    from conftest import parboil_compare
+    for name in ("small", "medium"):
+        d = parboil[name]
+        y = _harness(libspmv, d["a"], d["x"], d["rowstr"], d["colidx"])
+        assert np.array_equal(y, oracle.spmv(d["a"], d["x"], d["rowstr"], d["colidx"])), name
+        assert parboil_compare(d["y_golden"], y), name
+    assert np.array_equal(_harness(libspmv, parboil["small"]["a"], parboil["small"]["x"],
+                                   parboil["small"]["rowstr"], parboil["small"]["colidx"]),
+                          parboil["small"]["y_golden"])
+
+
+def test_reference_callers_relinked_unchanged(libspmv, oracle, tmp_path):
+    """The reference's own parboil spmv CPU program and bfs, compiled from the
+    reference sources and linked against b200.so instead of libnative-spmv.so
+    (oracle/Makefile `relink`), run on the reference's inputs."""
+    import os
+    from pathlib import Path
+    golden = Path(__file__).resolve().parent / "golden"
+    ref_dir = oracle.REF_TEST_BIN.parent
+    pb, bfs = ref_dir / "parboil_spmv.b200", ref_dir / "bfs.b200"
+    if not pb.exists() or not bfs.exists():
+        pytest.skip("relinked reference binaries not built (reference tree absent at build time)")
+    out = tmp_path / "y.out"
+    proc = subprocess.run([str(pb), "-i", f"{golden / 'parboil_small_1138_bus.mtx'},"
+                           f"{golden / 'parboil_small_vector.bin'}", "-o", str(out)],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout
+    assert out.read_bytes() == (golden / "parboil_small_1138_bus.mtx.out").read_bytes()
+    with open(golden / "bfs_input.mtx") as fin:
+        proc = subprocess.run([str(bfs)], stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout
+    assert float(proc.stdout.strip().splitlines()[-1]) > 0.0

@@ -67,3 +67,16 @@ def test_extended_metric(oracle):
     y_ld, mag = oracle.spmv_extended(a, x, rowstr, c)
     nz = mag > 0
     assert np.all(np.abs(y - y_ld)[nz] <= 1e-14 * mag[nz])
+
+
+def test_oracle_fp32_against_parboil_golden_outputs(oracle, parboil):
+    """fp32 path pinned on the reference's parboil golden files: the small
+    dataset is reproduced bit for bit, the medium one within the reference's
+    own checker tolerance (tools/compare-output)."""
+    from conftest import parboil_compare
+    s = parboil["small"]
+    y = oracle.spmv(s["a"], s["x"], s["rowstr"], s["colidx"])
+    assert np.array_equal(y, s["y_golden"])
+    m = parboil["medium"]
+    y = oracle.spmv(m["a"], m["x"], m["rowstr"], m["colidx"])
+    assert parboil_compare(m["y_golden"], y)
