@@ -39,7 +39,7 @@ def build_product(quiet=True):
 
 
 def build_callers(quiet=True):
-    return _make(CALLERS, "libb200callers.so", "cg", quiet=quiet)
+    return _make(CALLERS, "all", quiet=quiet)
 
 
 def build_oracle(quiet=True):
