@@ -376,6 +376,14 @@ def run_b200(args, world, rank, local_rank):
             line["npb_cg"] = {"class": workload, "mops": res["mops"], "time_s": res["t_bench"],
                               "zeta": res["zeta"], "verified": res["verified"],
                               "spmv_calls": res["spmv_calls"], "vectors": "pageable host (as cg.f COMMON)"}
+        if not args.no_npb:
+            cls_ = npb.cg_class(workload)
+            dev = rm.npb_cg_device(cls_.nonzer, cls_.niter, cls_.shift, use_graph=True)
+            line["npb_cg_device_resident"] = {
+                "class": workload, "mops": dev["mops"], "time_s": dev["seconds"], "zeta": dev["zeta"],
+                "verified": bool(abs(dev["zeta"] - cls_.zeta_verify) / cls_.zeta_verify <= 1e-10),
+                "spmv_launches": dev["spmv_launches"], "vector_launches": dev["vector_launches"],
+                "note": "vectors resident in HBM, CUDA graph per conj_grad (include/b200_cg.h)"}
         if not args.no_cpu:
             x_host = xs[0].cpu().numpy()
             nsamp = args.cpu_steps

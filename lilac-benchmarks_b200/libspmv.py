@@ -21,6 +21,11 @@ KERNEL_IDS = {"auto": 0, "ordered": 1, "vector": 2, "panel": 3, "merge": 4, "sel
 F64, F32 = 0, 1
 
 
+class CgResult(C.Structure):
+    _fields_ = [("zeta", c_double), ("rnorm", c_double), ("seconds", c_double), ("mops", c_double),
+                ("spmv_launches", c_int), ("vector_launches", c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [("calls", c_uint64), ("uploads", c_uint64), ("kernel_launches", c_uint64),
                 ("kernel_ms", c_double), ("e2e_ms", c_double), ("upload_ms", c_double),
@@ -74,6 +79,21 @@ def lib():
     L.b200_spmv_unpin_host.restype = c_int
     L.b200_spmv_version.argtypes = []
     L.b200_spmv_version.restype = c_char_p
+    # include/b200_cg.h
+    L.b200_cg_npb_run.argtypes = [c_void_p, c_int, c_int, c_double, c_int, POINTER(c_double),
+                                  POINTER(c_double), POINTER(CgResult)]
+    L.b200_cg_npb_run.restype = c_int
+    L.b200_cg_partials.argtypes = []
+    L.b200_cg_partials.restype = c_int
+    L.b200_cg_dot.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    L.b200_cg_dot.restype = None
+    L.b200_cg_update_zr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]
+    L.b200_cg_update_zr.restype = None
+    L.b200_cg_update_p.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.b200_cg_update_p.restype = None
+    L.b200_cg_finish.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.b200_cg_finish.restype = None
     _lib = L
     return L
 
@@ -181,6 +201,19 @@ class ResidentMatrix:
         assert x.is_cuda and y.is_cuda and x.is_contiguous() and y.is_contiguous()
         assert x.numel() >= self.ncols and y.numel() >= self.rows
         return self.exec_ptr(x.data_ptr(), y.data_ptr(), stream)
+
+    def npb_cg_device(self, nonzer, niter, shift, use_graph=True):
+        """Whole NPB CG benchmark with every vector resident in HBM (include/b200_cg.h)."""
+        zeta_hist = np.zeros(niter)
+        rnorm_hist = np.zeros(niter)
+        res = CgResult()
+        rc = lib().b200_cg_npb_run(self._h, int(nonzer), int(niter), float(shift), int(bool(use_graph)),
+                                   _ptr(zeta_hist, c_double), _ptr(rnorm_hist, c_double), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"b200_cg_npb_run failed with {rc}")
+        return {"zeta": res.zeta, "rnorm": res.rnorm, "seconds": res.seconds, "mops": res.mops,
+                "spmv_launches": res.spmv_launches, "vector_launches": res.vector_launches,
+                "zeta_hist": zeta_hist, "rnorm_hist": rnorm_hist}
 
     def row_histogram(self):
         bins = (c_int64 * 32)()

@@ -346,3 +346,22 @@ def test_reference_callers_relinked_unchanged(libspmv, oracle, tmp_path):
                               text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout
     assert float(proc.stdout.strip().splitlines()[-1]) > 0.0
+
+
+@pytest.mark.parametrize("cls,use_graph", [("S", False), ("S", True), ("A", True), ("B", True)])
+def test_device_resident_npb_cg_verifies(libspmv, npb, npb_history, cls, use_graph):
+    """include/b200_cg.h: NPB CG with x, z, p, q, r resident in HBM.  zeta
+    verifies against cg.f:122-166 (1e-10); the per-iteration zeta agrees with
+    the host-algebra history to the accuracy the re-ordered dot products allow."""
+    m = npb.NpbMatrix(cls)
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+    res = rm.npb_cg_device(m.cls.nonzer, m.cls.niter, m.cls.shift, use_graph=use_graph)
+    ref = npb_history["zeta_verify"][cls]
+    assert abs(res["zeta"] - ref) / ref <= 1e-10
+    assert res["spmv_launches"] == 26 * m.cls.niter * rm.launches_per_exec
+    if cls in npb_history["classes"]:
+        gold = np.array([float(z) for z in npb_history["classes"][cls]["zeta"]])
+        assert np.allclose(res["zeta_hist"], gold, rtol=1e-9, atol=0)
+    # deterministic run to run (fixed reduction order, no atomics)
+    res2 = rm.npb_cg_device(m.cls.nonzer, m.cls.niter, m.cls.shift, use_graph=use_graph)
+    assert np.array_equal(res["zeta_hist"], res2["zeta_hist"])
