@@ -191,7 +191,7 @@ def run_reference_arm(args, world, rank):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------
@@ -369,6 +369,25 @@ def run_b200(args, world, rank, local_rank):
             "clocks": clocks,
         }
 
+    # ---- NPB CG, device-resident and row-block sharded (N > 1) --------------
+    if world > 1 and not args.no_npb:
+        cls_ = npb.cg_class(workload)
+        cg = sharded.ShardedNpbCg(sh, sharded.B200VectorOps(libspmv, dev), cls_.shift)
+        zeta_h, rnorm_h, cg_sec = cg.run(cls_.niter, sync=barrier)
+        tt = torch.tensor([cg_sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cg_sec = float(tt.item())
+        if rank == 0:
+            nz1 = cls_.nonzer * (cls_.nonzer + 1)
+            mops = 2.0 * cls_.niter * cls_.na * (3.0 + nz1 + 25.0 * (5.0 + nz1) + 3.0) / cg_sec / 1e6
+            line["npb_cg_device_resident"] = {
+                "class": workload, "mops": mops, "time_s": cg_sec, "zeta": zeta_h[-1],
+                "verified": bool(abs(zeta_h[-1] - cls_.zeta_verify) / cls_.zeta_verify <= 1e-10),
+                "spmv_launches_per_rank": cg.spmv_count * rm.launches_per_exec,
+                "collectives": cg.collectives,
+                "note": "row-block sharded vectors resident in HBM; per CG iteration: allgather of p + "
+                        "2 one-scalar allreduces (NCCL)"}
+
     # ---- NPB CG whole benchmark through the ABI + CPU baseline (N = 1) ----
     if world == 1 and rank == 0:
         if not args.no_npb:
@@ -400,13 +419,18 @@ def run_b200(args, world, rank, local_rank):
                 "value": B / dt_omp / 1e9, "unit": UNIT, "cores": cores_omp, "kind": "port",
                 "note": "row-parallel OpenMP loop, stand-in for libspmv/mkl.c (MKL not in image)"}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # Everything a library prints on stdout (NCCL's version banner, for one) goes to
+    # stderr; the one JSON line is written to the real stdout at the end.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)

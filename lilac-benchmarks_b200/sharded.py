@@ -97,3 +97,138 @@ class ShardedSpmv:
         x_full = self.assemble_x(x_local)
         self.local_spmv(x_full, self.y_local)
         return self.y_local
+
+
+# ---------------------------------------------------------------------------
+# Device-resident NPB CG over row blocks (SURVEY.md section 8e "device-resident
+# CG mode", section 8f row 1): every rank keeps its slices of x, z, p, q, r in
+# HBM; per CG iteration the ranks allgather their p slices, run the local
+# product, and complete the two dot products with an allreduce of one scalar.
+# Follows NPB3.3.1/CG/cg.f:447-644 (conj_grad) and :299-349 (outer loop).
+# ---------------------------------------------------------------------------
+class TorchVectorOps:
+    """Vector algebra of conj_grad with plain torch ops (CPU gloo tests)."""
+
+    def dot(self, x, y):
+        return (x * y).sum().reshape(1)
+
+    def update_zr(self, z, r, p, q, rho, d):
+        alpha = rho / d
+        z.add_(alpha * p)
+        r.sub_(alpha * q)
+        return (r * r).sum().reshape(1)
+
+    def update_p(self, p, r, rho_new, rho_old):
+        beta = rho_new / rho_old
+        p.mul_(beta).add_(r)
+
+
+class B200VectorOps:
+    """The same through the fused CUDA kernels of include/b200_cg.h (torch only
+    owns the memory and the stream)."""
+
+    def __init__(self, libspmv_module, device):
+        import torch
+        self.torch = torch
+        self.L = libspmv_module.lib()
+        nb = self.L.b200_cg_partials()
+        self.partial = torch.zeros(nb, dtype=torch.float64, device=device)
+        self.device = device
+
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _finish(self):
+        out = self.torch.empty(1, dtype=self.torch.float64, device=self.device)
+        self.L.b200_cg_finish(self.partial.data_ptr(), out.data_ptr(), self._stream())
+        return out
+
+    def dot(self, x, y):
+        self.L.b200_cg_dot(x.data_ptr(), y.data_ptr(), x.numel(), self.partial.data_ptr(), self._stream())
+        return self._finish()
+
+    def update_zr(self, z, r, p, q, rho, d):
+        self.L.b200_cg_update_zr(z.data_ptr(), r.data_ptr(), p.data_ptr(), q.data_ptr(), z.numel(),
+                                 rho.data_ptr(), d.data_ptr(), self.partial.data_ptr(), self._stream())
+        return self._finish()
+
+    def update_p(self, p, r, rho_new, rho_old):
+        self.L.b200_cg_update_p(p.data_ptr(), r.data_ptr(), p.numel(), rho_new.data_ptr(),
+                                rho_old.data_ptr(), self._stream())
+
+
+class ShardedNpbCg:
+    """NPB CG with row-block sharded, device-resident vectors."""
+
+    def __init__(self, sharded_spmv, ops, shift, cgitmax=25):
+        self.sp = sharded_spmv
+        self.ops = ops
+        self.shift = shift
+        self.cgitmax = cgitmax
+        t = sharded_spmv.torch
+        n_local = sharded_spmv.hi - sharded_spmv.lo
+        dev, dt = sharded_spmv.y_local.device, sharded_spmv.y_local.dtype
+        self.x, self.z, self.p, self.q, self.r = (t.zeros(n_local, dtype=dt, device=dev) for _ in range(5))
+        self.spmv_count = 0
+        self.collectives = 0
+
+    def _allreduce(self, v):
+        if self.sp.dist is not None and self.sp.layout.parts > 1:
+            self.sp.dist.all_reduce(v)
+            self.collectives += 1
+        return v
+
+    def _product(self, src, dst):
+        dst.copy_(self.sp.step(src))
+        self.spmv_count += 1
+        if self.sp.layout.parts > 1:
+            self.collectives += 1
+
+    def conj_grad(self):
+        """cg.f:447-644; returns ||x - A z|| as a 1-element tensor."""
+        ops = self.ops
+        self.q.zero_()
+        self.z.zero_()
+        self.r.copy_(self.x)
+        self.p.copy_(self.r)
+        rho = self._allreduce(ops.dot(self.r, self.r))
+        for _ in range(self.cgitmax):
+            self._product(self.p, self.q)                              # q = A p
+            d = self._allreduce(ops.dot(self.p, self.q))
+            rho_new = self._allreduce(ops.update_zr(self.z, self.r, self.p, self.q, rho, d))
+            ops.update_p(self.p, self.r, rho_new, rho)
+            rho = rho_new
+        self._product(self.z, self.r)                                  # r = A z
+        diff = self.x - self.r
+        return self._allreduce(ops.dot(diff, diff)).sqrt()
+
+    def run(self, niter, untimed_first=True, sync=None):
+        """cg.f:216-352.  Returns (zeta history, rnorm history, seconds of the timed loop)."""
+        import time
+        t = self.sp.torch
+        hist_z, hist_r = [], []
+
+        def outer():
+            rnorm = self.conj_grad()
+            nt = t.cat([self.ops.dot(self.x, self.z), self.ops.dot(self.z, self.z)])
+            nt = self._allreduce(nt)
+            self.x.copy_(self.z / nt[1].sqrt())
+            return rnorm, nt
+
+        if untimed_first:
+            self.x.fill_(1.0)
+            outer()
+        self.x.fill_(1.0)
+        self.spmv_count = 0
+        self.collectives = 0
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        for _ in range(niter):
+            rnorm, nt = outer()
+            vals = t.cat([rnorm, nt]).cpu()          # one small device->host read per outer iteration
+            hist_r.append(float(vals[0]))
+            hist_z.append(self.shift + 1.0 / float(vals[1]))
+        if sync:
+            sync()
+        return hist_z, hist_r, time.perf_counter() - t0

@@ -103,3 +103,51 @@ def test_layout_helpers():
     assert lay.slot == 5 and not lay.contiguous and lay.local_range(1) == (2, 7)
     lay = sharded.ShardLayout.build(1500000, 8)
     assert lay.contiguous and lay.slot == 187500
+
+
+def _cg_worker(rank, world, port, cls, out_dir):
+    sys.path.insert(0, str(ROOT))
+    import __graft_entry__ as entry
+    entry.load_package()
+    oracle = entry.load_oracle()
+    from lilac_benchmarks_b200 import npb, sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = npb.cg_class(cls)
+        layout = sharded.ShardLayout.build(c.na, world)
+        lo, hi = layout.local_range(rank)
+        blk = npb.NpbMatrix(cls, lo, hi)
+
+        def local_spmv(x_full, y_local):
+            y_local.copy_(torch.from_numpy(oracle.spmv(blk.a, x_full.numpy(), blk.rowstr, blk.colidx)))
+
+        sh = sharded.ShardedSpmv(layout, rank, local_spmv, dist=dist)
+        cg = sharded.ShardedNpbCg(sh, sharded.TorchVectorOps(), c.shift)
+        zeta, rnorm, _ = cg.run(c.niter)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "zeta.npy"), np.array(zeta))
+            np.save(os.path.join(out_dir, "counts.npy"), np.array([cg.spmv_count, cg.collectives]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_device_resident_cg_verifies_on_two_ranks(tmp_path):
+    """The multi-rank CG driver (allgather of p + allreduce of the dot products)
+    reaches NPB's zeta for class S on a world_size-2 gloo group."""
+    sys.path.insert(0, str(ROOT))
+    import __graft_entry__ as entry
+    entry.build()
+    entry.load_package()
+    from lilac_benchmarks_b200 import npb
+    mp.spawn(_cg_worker, args=(2, _free_port(), "S", str(tmp_path)), nprocs=2, join=True)
+    c = npb.cg_class("S")
+    zeta = np.load(tmp_path / "zeta.npy")
+    assert len(zeta) == c.niter
+    assert abs(zeta[-1] - c.zeta_verify) / c.zeta_verify <= 1e-10
+    spmv, coll = np.load(tmp_path / "counts.npy")
+    assert spmv == 26 * c.niter
+    # per conj_grad: 26 allgathers + 1 + 25*2 + 1 allreduces, plus 1 for the norms
+    assert coll == c.niter * (26 + 1 + 50 + 1 + 1)
