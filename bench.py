@@ -372,11 +372,26 @@ def run_b200(args, world, rank, local_rank):
     # ---- NPB CG, device-resident and row-block sharded (N > 1) --------------
     if world > 1 and not args.no_npb:
         cls_ = npb.cg_class(workload)
-        cg = sharded.ShardedNpbCg(sh, sharded.B200VectorOps(libspmv, dev), cls_.shift)
-        zeta_h, rnorm_h, cg_sec = cg.run(cls_.niter, sync=barrier)
-        tt = torch.tensor([cg_sec], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cg_sec = float(tt.item())
+        def run_cg(kind):
+            if kind == "peer":
+                drv = sharded.PeerNpbCg(libspmv, rm, layout, rank, cls_.shift, dist=dist, device=dev)
+            else:
+                drv = sharded.ShardedNpbCg(sh, sharded.B200VectorOps(libspmv, dev), cls_.shift)
+            zh, rh, sec = drv.run(cls_.niter, sync=barrier)
+            tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            count = drv.spmv_count
+            if kind == "peer":
+                drv.close()
+            return zh, float(tt.item()), count
+
+        zeta_nccl, sec_nccl, _ = run_cg("nccl")
+        zeta_h, cg_sec, spmv_count = run_cg("peer")
+
+        class _Cnt:
+            pass
+        cg = _Cnt()
+        cg.spmv_count, cg.collectives = spmv_count, 0
         if rank == 0:
             nz1 = cls_.nonzer * (cls_.nonzer + 1)
             mops = 2.0 * cls_.niter * cls_.na * (3.0 + nz1 + 25.0 * (5.0 + nz1) + 3.0) / cg_sec / 1e6
@@ -385,8 +400,10 @@ def run_b200(args, world, rank, local_rank):
                 "verified": bool(abs(zeta_h[-1] - cls_.zeta_verify) / cls_.zeta_verify <= 1e-10),
                 "spmv_launches_per_rank": cg.spmv_count * rm.launches_per_exec,
                 "collectives": cg.collectives,
-                "note": "row-block sharded vectors resident in HBM; per CG iteration: allgather of p + "
-                        "2 one-scalar allreduces (NCCL)"}
+                "exchange": "fused into the update / dot kernels over NVLink peer memory "
+                            "(include/b200_peer.h), no NCCL call inside conj_grad",
+                "nccl_variant": {"time_s": sec_nccl, "zeta": zeta_nccl[-1],
+                                 "exchange": "allgather of p + 2 one-scalar allreduces per CG iteration"}}
 
     # ---- NPB CG whole benchmark through the ABI + CPU baseline (N = 1) ----
     if world == 1 and rank == 0:

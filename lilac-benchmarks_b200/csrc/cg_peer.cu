@@ -1,0 +1,346 @@
+/*
+ * cg_peer.cu -- fused compute + exchange kernels over peer memory
+ * (include/b200_peer.h).  The algebra is conj_grad of NPB3.3.1/CG/cg.f:447-644;
+ * the exchange replaces what an MPI / NCCL version would do with an allgather
+ * of p and two allreduces per CG iteration.
+ *
+ * Memory model: data stores to peers are plain st.global; after its stores a
+ * block executes __threadfence_system() and bumps a local counter; the block
+ * that finishes last publishes the epoch to every rank with st.release.sys.
+ * Consumers spin with ld.acquire.sys.  One rank per GPU, so a spinning kernel
+ * never waits on work queued behind it on its own device.
+ */
+#include "../../include/b200_peer.h"
+
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kBlocks = 296;
+constexpr int kThreads = 256;
+constexpr int NR = B200_PEER_MAX_RANKS;
+
+#define PEER_OK(call)                                                          \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            fprintf(stderr, "libb200-spmv: fatal: %s failed at %s:%d: %s\n", #call, __FILE__,     \
+                    __LINE__, cudaGetErrorString(e_));                         \
+            abort();                                                           \
+        }                                                                      \
+    } while (0)
+
+/* device view of the group: pointers into every rank's segment */
+struct PeerDev {
+    int rank, nranks;
+    double *xfull[NR];
+    double *scal[NR];                   /* [B200_PEER_SLOTS][NR] */
+    unsigned long long *sflag[NR];      /* [B200_PEER_SLOTS][NR] */
+    unsigned long long *vflag[NR];      /* [NR] */
+    unsigned int *counter;              /* local: last-block detection, one per kernel kind */
+    double *partial;                    /* local: kBlocks doubles */
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double red[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+    }
+    __syncthreads();
+    return s;
+}
+
+/* true in every thread of the block that arrives last (all other blocks'
+ * earlier global / peer stores are then visible to it and ordered before
+ * whatever it publishes) */
+__device__ __forceinline__ bool last_block(unsigned int *counter)
+{
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        last = prev == gridDim.x - 1;
+        if (last) *counter = 0;                  /* ready for the next launch */
+    }
+    __syncthreads();
+    if (last) __threadfence_system();
+    return last;
+}
+
+/* spin until every rank published >= e in my flag row */
+__device__ __forceinline__ void wait_flags(const unsigned long long *flags, int nranks,
+                                           unsigned long long e)
+{
+    if (threadIdx.x < nranks)
+        while (ld_acquire_sys(flags + threadIdx.x) < e) { }
+    __syncthreads();
+}
+
+/* rank-ordered sum of a scalar slot in my segment (same bits on every rank) */
+__device__ __forceinline__ double slot_sum(const PeerDev &g, int slot)
+{
+    const double *s = g.scal[g.rank] + slot * NR;
+    double t = 0.0;
+    for (int r = 0; r < g.nranks; ++r) t += s[r];
+    return t;
+}
+
+/* the last block reduces the block partials in fixed order and publishes */
+__device__ __forceinline__ void publish_scalar(const PeerDev &g, int slot, unsigned long long e,
+                                               unsigned int *counter)
+{
+    if (last_block(counter)) {
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) t += g.partial[b];
+            for (int j = 0; j < g.nranks; ++j) g.scal[j][slot * NR + g.rank] = t;
+            __threadfence_system();
+            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.sflag[j] + slot * NR + g.rank, e);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e)
+{
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double val = v[i];
+        for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
+    }
+    if (last_block(g.counter + 0) && threadIdx.x == 0)
+        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+}
+
+__global__ void peer_wait_vector_kernel(PeerDev g, unsigned long long e)
+{
+    wait_flags(g.vflag[g.rank], g.nranks, e);
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_dot_kernel(PeerDev g, const double *__restrict__ x, const double *__restrict__ y, int n, int mode,
+                int slot, unsigned long long e)
+{
+    double acc = 0.0;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        if (mode == 0) acc += x[i] * y[i];
+        else { const double d = x[i] - y[i]; acc += d * d; }
+    }
+    const double s = block_sum(acc);
+    if (threadIdx.x == 0) g.partial[blockIdx.x] = s;
+    publish_scalar(g, slot, e, g.counter + 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_update_zr_kernel(PeerDev g, double *z, double *r, const double *__restrict__ p,
+                      const double *__restrict__ q, int n, int slot_rho, int slot_d,
+                      unsigned long long e_d, int slot_out, unsigned long long e_out)
+{
+    wait_flags(g.sflag[g.rank] + slot_d * NR, g.nranks, e_d);
+    const double alpha = slot_sum(g, slot_rho) / slot_sum(g, slot_d);          /* cg.f:581 */
+    double acc = 0.0;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        z[i] = z[i] + alpha * p[i];                                            /* cg.f:593-596 */
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        acc += ri * ri;                                                        /* cg.f:602-604 */
+    }
+    const double s = block_sum(acc);
+    if (threadIdx.x == 0) g.partial[blockIdx.x] = s;
+    publish_scalar(g, slot_out, e_out, g.counter + 2);
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_update_p_kernel(PeerDev g, double *p, const double *__restrict__ r, int n, long long lo,
+                     int slot_new, unsigned long long e_new, int slot_old, unsigned long long e_vec)
+{
+    wait_flags(g.sflag[g.rank] + slot_new * NR, g.nranks, e_new);
+    const double beta = slot_sum(g, slot_new) / slot_sum(g, slot_old);         /* cg.f:609 */
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double pi = r[i] + beta * p[i];                                  /* cg.f:614-616 */
+        p[i] = pi;
+        /* the exchange: every rank's copy of the full vector gets the element now */
+        for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = pi;
+    }
+    if (last_block(g.counter + 3) && threadIdx.x == 0)
+        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e_vec);
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_scale_kernel(PeerDev g, double *x, const double *__restrict__ z, int n, int slot,
+                  unsigned long long e)
+{
+    wait_flags(g.sflag[g.rank] + slot * NR, g.nranks, e);
+    const double s = 1.0 / sqrt(slot_sum(g, slot));                            /* cg.f:322, 344-346 */
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) x[i] = s * z[i];
+}
+
+struct SlotList { int slot[B200_PEER_SLOTS]; unsigned long long epoch[B200_PEER_SLOTS]; int count; };
+
+__global__ void peer_read_slots_kernel(PeerDev g, SlotList l, double *out)
+{
+    for (int k = 0; k < l.count; ++k) {
+        wait_flags(g.sflag[g.rank] + l.slot[k] * NR, g.nranks, l.epoch[k]);
+        if (threadIdx.x == 0) out[k] = slot_sum(g, l.slot[k]);
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+struct b200_peer_group {
+    int rank, nranks;
+    int64_t n_global;
+    size_t bytes;
+    char *local;                 /* my segment */
+    char *peer[NR];              /* mapped segments (peer[rank] == local) */
+    unsigned int *counter;
+    double *partial;
+    PeerDev dev;
+    bool connected;
+};
+
+static size_t seg_x_bytes(int64_t n) { return (((size_t)n + 2) * sizeof(double) + 255) & ~(size_t)255; }
+static size_t seg_scal_off(int64_t n) { return seg_x_bytes(n); }
+static size_t seg_sflag_off(int64_t n) { return seg_scal_off(n) + B200_PEER_SLOTS * NR * sizeof(double); }
+static size_t seg_vflag_off(int64_t n) { return seg_sflag_off(n) + B200_PEER_SLOTS * NR * sizeof(unsigned long long); }
+static size_t seg_total(int64_t n) { return seg_vflag_off(n) + NR * sizeof(unsigned long long) + 256; }
+
+static void fill_dev(b200_peer_group *g)
+{
+    PeerDev &d = g->dev;
+    d.rank = g->rank;
+    d.nranks = g->nranks;
+    for (int j = 0; j < g->nranks; ++j) {
+        d.xfull[j] = (double *)g->peer[j];
+        d.scal[j] = (double *)(g->peer[j] + seg_scal_off(g->n_global));
+        d.sflag[j] = (unsigned long long *)(g->peer[j] + seg_sflag_off(g->n_global));
+        d.vflag[j] = (unsigned long long *)(g->peer[j] + seg_vflag_off(g->n_global));
+    }
+    d.counter = g->counter;
+    d.partial = g->partial;
+}
+
+extern "C" b200_peer_group *b200_peer_create(int rank, int nranks, int64_t n_global, void *ipc_handle_out)
+{
+    if (nranks < 1 || nranks > NR || rank < 0 || rank >= nranks) return nullptr;
+    b200_peer_group *g = (b200_peer_group *)calloc(1, sizeof *g);
+    g->rank = rank; g->nranks = nranks; g->n_global = n_global;
+    g->bytes = seg_total(n_global);
+    PEER_OK(cudaMalloc((void **)&g->local, g->bytes));
+    PEER_OK(cudaMemset(g->local, 0, g->bytes));
+    PEER_OK(cudaMalloc((void **)&g->counter, 8 * sizeof(unsigned int)));
+    PEER_OK(cudaMemset(g->counter, 0, 8 * sizeof(unsigned int)));
+    PEER_OK(cudaMalloc((void **)&g->partial, kBlocks * sizeof(double)));
+    g->peer[rank] = g->local;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof h);
+        if (nranks > 1) PEER_OK(cudaIpcGetMemHandle(&h, g->local));
+        static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+        memcpy(ipc_handle_out, &h, sizeof h);
+    }
+    if (nranks == 1) { fill_dev(g); g->connected = true; }
+    return g;
+}
+
+extern "C" int b200_peer_connect(b200_peer_group *g, const void *handles)
+{
+    for (int j = 0; j < g->nranks; ++j) {
+        if (j == g->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)j * B200_IPC_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "libb200-spmv: cudaIpcOpenMemHandle(rank %d) failed: %s\n", j,
+                    cudaGetErrorString(e));
+            return -1;
+        }
+        g->peer[j] = (char *)p;
+    }
+    fill_dev(g);
+    g->connected = true;
+    return 0;
+}
+
+extern "C" void b200_peer_destroy(b200_peer_group *g)
+{
+    if (!g) return;
+    cudaDeviceSynchronize();
+    for (int j = 0; j < g->nranks; ++j)
+        if (j != g->rank && g->peer[j]) cudaIpcCloseMemHandle(g->peer[j]);
+    cudaFree(g->local); cudaFree(g->counter); cudaFree(g->partial);
+    free(g);
+}
+
+extern "C" double *b200_peer_xfull(b200_peer_group *g) { return (double *)g->local; }
+
+extern "C" void b200_peer_push(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
+                               void *stream)
+{
+    peer_push_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e);
+}
+
+extern "C" void b200_peer_wait_vector(b200_peer_group *g, uint64_t e, void *stream)
+{
+    peer_wait_vector_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->dev, e);
+}
+
+extern "C" void b200_peer_dot(b200_peer_group *g, const double *x, const double *y, int n_local, int mode,
+                              int slot, uint64_t e, void *stream)
+{
+    peer_dot_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, x, y, n_local, mode, slot, e);
+}
+
+extern "C" void b200_peer_update_zr(b200_peer_group *g, double *z, double *r, const double *p,
+                                    const double *q, int n_local, int slot_rho, int slot_d, uint64_t e_d,
+                                    int slot_out, uint64_t e_out, void *stream)
+{
+    peer_update_zr_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(
+        g->dev, z, r, p, q, n_local, slot_rho, slot_d, e_d, slot_out, e_out);
+}
+
+extern "C" void b200_peer_update_p(b200_peer_group *g, double *p, const double *r, int n_local, int64_t lo,
+                                   int slot_new, uint64_t e_new, int slot_old, uint64_t e_vec, void *stream)
+{
+    peer_update_p_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(
+        g->dev, p, r, n_local, (long long)lo, slot_new, e_new, slot_old, e_vec);
+}
+
+extern "C" void b200_peer_scale(b200_peer_group *g, double *x, const double *z, int n_local, int slot,
+                                uint64_t e, void *stream)
+{
+    peer_scale_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, x, z, n_local, slot, e);
+}
+
+extern "C" void b200_peer_read_slots(b200_peer_group *g, const int *slots, const uint64_t *epochs,
+                                     int count, double *out, void *stream)
+{
+    SlotList l;
+    l.count = count > B200_PEER_SLOTS ? B200_PEER_SLOTS : count;
+    for (int k = 0; k < l.count; ++k) { l.slot[k] = slots[k]; l.epoch[k] = epochs[k]; }
+    peer_read_slots_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->dev, l, out);
+}

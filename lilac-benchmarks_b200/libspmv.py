@@ -94,6 +94,27 @@ def lib():
     L.b200_cg_update_p.restype = None
     L.b200_cg_finish.argtypes = [c_void_p, c_void_p, c_void_p]
     L.b200_cg_finish.restype = None
+    # include/b200_peer.h
+    u64 = C.c_uint64
+    L.b200_peer_create.argtypes = [c_int, c_int, c_int64, c_void_p]
+    L.b200_peer_create.restype = c_void_p
+    L.b200_peer_connect.argtypes = [c_void_p, c_void_p]
+    L.b200_peer_connect.restype = c_int
+    L.b200_peer_destroy.argtypes = [c_void_p]
+    L.b200_peer_destroy.restype = None
+    L.b200_peer_xfull.argtypes = [c_void_p]
+    L.b200_peer_xfull.restype = c_void_p
+    L.b200_peer_push.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, c_void_p]
+    L.b200_peer_wait_vector.argtypes = [c_void_p, u64, c_void_p]
+    L.b200_peer_dot.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, u64, c_void_p]
+    L.b200_peer_update_zr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, u64, c_int, u64, c_void_p]
+    L.b200_peer_update_p.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, u64, c_int,
+                                     u64, c_void_p]
+    L.b200_peer_scale.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, u64, c_void_p]
+    L.b200_peer_read_slots.argtypes = [c_void_p, POINTER(c_int), POINTER(u64), c_int, c_void_p, c_void_p]
+    for nm in ("push", "wait_vector", "dot", "update_zr", "update_p", "scale", "read_slots"):
+        getattr(L, "b200_peer_" + nm).restype = None
     _lib = L
     return L
 

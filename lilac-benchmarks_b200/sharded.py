@@ -232,3 +232,115 @@ class ShardedNpbCg:
         if sync:
             sync()
         return hist_z, hist_r, time.perf_counter() - t0
+
+
+# ---------------------------------------------------------------------------
+# The same CG with the exchanges fused into the producing kernels over NVLink
+# peer memory (include/b200_peer.h): no NCCL call and no host synchronisation
+# inside conj_grad.  torch.distributed is used once, to swap the IPC handles.
+# ---------------------------------------------------------------------------
+class PeerNpbCg:
+    RHO = (0, 1)       # ping-pong slots for rho
+    D, XZ, ZZ, RES = 2, 3, 4, 5
+
+    def __init__(self, libspmv_module, resident_matrix, layout, rank, shift, dist=None, device="cuda",
+                 cgitmax=25):
+        import ctypes as C
+        import torch
+        self.torch, self.C = torch, C
+        self.L = libspmv_module.lib()
+        self.rm = resident_matrix
+        self.layout, self.rank, self.shift, self.cgitmax = layout, rank, shift, cgitmax
+        self.lo, self.hi = layout.local_range(rank)
+        self.n_local = self.hi - self.lo
+        world = layout.parts
+        handle = (C.c_ubyte * 64)()
+        self.g = self.L.b200_peer_create(rank, world, layout.rows, handle)
+        if not self.g:
+            raise RuntimeError("b200_peer_create failed")
+        if world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = torch.empty(64 * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine)
+            buf = (C.c_ubyte * (64 * world))(*allh.cpu().tolist())
+            if self.L.b200_peer_connect(self.g, buf) != 0:
+                raise RuntimeError("b200_peer_connect failed (no peer access between the GPUs?)")
+            dist.barrier()
+        self.xfull = self.L.b200_peer_xfull(self.g)
+        mk = lambda: torch.zeros(self.n_local, dtype=torch.float64, device=device)   # noqa: E731
+        self.x, self.z, self.p, self.q, self.r = mk(), mk(), mk(), mk(), mk()
+        self.out = torch.zeros(4, dtype=torch.float64, device=device)
+        self.epoch = 0
+        self.spmv_count = 0
+        self.dist = dist
+
+    def close(self):
+        if self.g:
+            self.torch.cuda.synchronize()
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.barrier()
+            self.L.b200_peer_destroy(self.g)
+            self.g = None
+
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _next(self):
+        self.epoch += 1
+        return self.epoch
+
+    def _spmv_from_xfull(self, e_vec, dst):
+        self.L.b200_peer_wait_vector(self.g, e_vec, self._s())
+        self.rm.exec_ptr(self.xfull, dst.data_ptr(), self._s())
+        self.spmv_count += 1
+
+    def outer_iteration(self):
+        """conj_grad (cg.f:447-644) + the zeta / normalisation step (cg.f:315-346);
+        leaves (x.z, residual sum) in self.out."""
+        L, g, n, lo, s = self.L, self.g, self.n_local, self.lo, self._s
+        x, z, p, q, r = self.x, self.z, self.p, self.q, self.r
+        q.zero_(); z.zero_(); r.copy_(x); p.copy_(r)
+        L.b200_peer_dot(g, r.data_ptr(), r.data_ptr(), n, 0, self.RHO[0], self._next(), s())
+        e_vec = self._next()
+        L.b200_peer_push(g, p.data_ptr(), n, lo, e_vec, s())
+        for it in range(self.cgitmax):
+            rho_old, rho_new = self.RHO[it & 1], self.RHO[(it + 1) & 1]
+            self._spmv_from_xfull(e_vec, q)                                        # q = A p
+            e_d = self._next()
+            L.b200_peer_dot(g, p.data_ptr(), q.data_ptr(), n, 0, self.D, e_d, s())
+            e_rho = self._next()
+            L.b200_peer_update_zr(g, z.data_ptr(), r.data_ptr(), p.data_ptr(), q.data_ptr(), n,
+                                  rho_old, self.D, e_d, rho_new, e_rho, s())
+            e_vec = self._next()
+            L.b200_peer_update_p(g, p.data_ptr(), r.data_ptr(), n, lo, rho_new, e_rho, rho_old, e_vec, s())
+        e_vec = self._next()
+        L.b200_peer_push(g, z.data_ptr(), n, lo, e_vec, s())
+        self._spmv_from_xfull(e_vec, r)                                            # r = A z
+        e_res, e_xz, e_zz = self._next(), self._next(), self._next()
+        L.b200_peer_dot(g, x.data_ptr(), r.data_ptr(), n, 1, self.RES, e_res, s())
+        L.b200_peer_dot(g, x.data_ptr(), z.data_ptr(), n, 0, self.XZ, e_xz, s())
+        L.b200_peer_dot(g, z.data_ptr(), z.data_ptr(), n, 0, self.ZZ, e_zz, s())
+        C = self.C
+        slots = (C.c_int * 2)(self.XZ, self.RES)
+        epochs = (C.c_uint64 * 2)(e_xz, e_res)
+        L.b200_peer_read_slots(g, slots, epochs, 2, self.out.data_ptr(), s())
+        L.b200_peer_scale(g, x.data_ptr(), z.data_ptr(), n, self.ZZ, e_zz, s())
+
+    def run(self, niter, sync=None):
+        import time
+        hist_z, hist_r = [], []
+        self.x.fill_(1.0)
+        self.outer_iteration()                     # untimed (cg.f:233-272)
+        self.x.fill_(1.0)
+        self.spmv_count = 0
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        for _ in range(niter):
+            self.outer_iteration()
+            vals = self.out.cpu()                  # the only host read per outer iteration
+            hist_z.append(self.shift + 1.0 / float(vals[0]))
+            hist_r.append(float(vals[1]) ** 0.5)
+        if sync:
+            sync()
+        return hist_z, hist_r, time.perf_counter() - t0

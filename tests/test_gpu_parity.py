@@ -365,3 +365,24 @@ def test_device_resident_npb_cg_verifies(libspmv, npb, npb_history, cls, use_gra
     # deterministic run to run (fixed reduction order, no atomics)
     res2 = rm.npb_cg_device(m.cls.nonzer, m.cls.niter, m.cls.shift, use_graph=use_graph)
     assert np.array_equal(res["zeta_hist"], res2["zeta_hist"])
+
+
+@pytest.mark.parametrize("cls", ["S", "A"])
+def test_peer_memory_cg_single_rank_group(libspmv, npb, npb_history, cls):
+    """include/b200_peer.h on a group of one rank: the fused update + exchange
+    kernels, the epoch flags and the slot reductions, with this GPU as its own
+    only peer.  zeta must verify (cg.f:122-166)."""
+    from lilac_benchmarks_b200 import sharded
+    m = npb.NpbMatrix(cls)
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+    layout = sharded.ShardLayout.build(m.n, 1)
+    cg = sharded.PeerNpbCg(libspmv, rm, layout, 0, m.cls.shift)
+    try:
+        zeta, rnorm, _ = cg.run(m.cls.niter)
+    finally:
+        cg.close()
+    ref = npb_history["zeta_verify"][cls]
+    assert abs(zeta[-1] - ref) / ref <= 1e-10
+    assert cg.spmv_count == 26 * m.cls.niter
+    gold = np.array([float(z) for z in npb_history["classes"][cls]["zeta"]])
+    assert np.allclose(zeta, gold, rtol=1e-9, atol=0)
