@@ -95,7 +95,7 @@ struct b200_matrix {
     void *d_pval; uint16_t *d_pcol; ushort4 *d_meta; int *d_slice_off;
     /* SELL layout (when kernel == B200_KERNEL_SELL) */
     DevSell sell;
-    int *d_scol; int *d_long_rows;
+    int *d_scol; int4 *d_chunks; int2 *d_multi; int *d_multi_rows; void *d_carry;
     /* staging owned by the drop-in path (allocated lazily) */
     void *d_x, *d_y;           /* device vectors */
     void *h_x, *h_y;           /* pinned bounce buffers */
@@ -346,7 +346,7 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
 }
 /* SELL layout: lane streams with global columns, x gathered through L2.
  * Applicable to every matrix; rows above the cap go to the long-row kernel. */
-static bool build_sell_locked(b200_matrix *m, const int *rowstr)
+static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_split)
 {
     if (m->rows <= 0 || m->nnz <= 0) return false;
     const size_t es = elem_size(m->dtype);
@@ -363,19 +363,35 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr)
     int cap = env_int("B200_SPMV_SELL_CAP", 0);
     if (cap <= 0) cap = (int)std::min(65534.0, std::max(64.0, 4.0 * mean));
     cap = std::min(cap, 65534);
+    if (all_rows_split) cap = 0;            /* MERGE: every row goes through the nnz-split path */
     const int nblk = (m->rows + R - 1) / R;
     const int Tn = R / G, spb = Tn / 32;
     const int nslices = nblk * spb;
     /* long rows (host pass over the caller's rowstr) */
-    std::vector<int> long_rows, huge_rows;
-    if (m->scan.max_len > cap)
+    /* long rows -> nnz-split chunks (host pass over the caller's rowstr) */
+    std::vector<int4> chunks;
+    std::vector<int2> multi;
+    std::vector<int> multi_rows;
+    int n_long = 0, n_carry = 0;
+    if (m->scan.max_len > cap) {
+        const int CH = sell_chunk_entries();
+        const int base = rowstr[0];
         for (int r = 0; r < m->rows; ++r) {
             const int len = rowstr[r + 1] - rowstr[r];
-            if (len > sell_warp_row_max()) huge_rows.push_back(r);
-            else if (len > cap) long_rows.push_back(r);
+            if (len <= cap) continue;
+            ++n_long;
+            const int lo = rowstr[r] - base, hi = rowstr[r + 1] - base;
+            const int nch = (len + CH - 1) / CH;
+            if (nch == 1) {
+                chunks.push_back(make_int4(r, lo, hi, -1));
+            } else {
+                multi.push_back(make_int2(n_carry, nch));
+                multi_rows.push_back(r);
+                for (int k = 0; k < nch; ++k)
+                    chunks.push_back(make_int4(r, lo + k * CH, std::min(hi, lo + (k + 1) * CH), n_carry++));
+            }
         }
-    const int n_long_warp = (int)long_rows.size();
-    long_rows.insert(long_rows.end(), huge_rows.begin(), huge_rows.end());
+    }
     uint16_t *d_seglen = nullptr;
     int *d_cnt = nullptr;
     const size_t nseg = (size_t)nblk * R;
@@ -407,14 +423,23 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr)
     sm.val = m->d_pval; sm.col = m->d_scol; sm.meta = m->d_meta; sm.slice_off = m->d_slice_off;
     sm.rows = m->rows; sm.R = R; sm.G = G; sm.nblk = nblk; sm.padded = run;
     sm.U = env_int("B200_SPMV_SELL_U", 2);
-    sm.n_long = (int)long_rows.size();
-    sm.n_long_warp = n_long_warp;
-    sm.long_rows = nullptr;
-    if (sm.n_long > 0) {
-        CUDA_OK(cudaMalloc((void **)&m->d_long_rows, long_rows.size() * sizeof(int)));
-        CUDA_OK(cudaMemcpyAsync(m->d_long_rows, long_rows.data(), long_rows.size() * sizeof(int),
-                                cudaMemcpyHostToDevice, g_stream));
-        sm.long_rows = m->d_long_rows;
+    sm.n_long = n_long;
+    sm.n_chunks = (int)chunks.size();
+    sm.n_multi = (int)multi.size();
+    sm.chunks = nullptr; sm.multi = nullptr; sm.multi_rows = nullptr; sm.carry = nullptr;
+    if (sm.n_chunks > 0) {
+        CUDA_OK(cudaMalloc((void **)&m->d_chunks, chunks.size() * sizeof(int4)));
+        CUDA_OK(cudaMemcpy(m->d_chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        sm.chunks = m->d_chunks;
+    }
+    if (sm.n_multi > 0) {
+        CUDA_OK(cudaMalloc((void **)&m->d_multi, multi.size() * sizeof(int2)));
+        CUDA_OK(cudaMemcpy(m->d_multi, multi.data(), multi.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc((void **)&m->d_multi_rows, multi_rows.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(m->d_multi_rows, multi_rows.data(), multi_rows.size() * sizeof(int),
+                           cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&m->d_carry, (size_t)std::max(n_carry, 1) * es));
+        sm.multi = m->d_multi; sm.multi_rows = m->d_multi_rows; sm.carry = m->d_carry;
     }
     if (m->dtype == B200_F64)
         launch_sell_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
@@ -427,7 +452,7 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr)
     CUDA_OK(cudaFree(d_seglen));
     m->resident_bytes = (int64_t)(nval * (es + 4) + (size_t)nblk * Tn * 8 + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
-    if (sm.n_long == 0) {
+    if (sm.n_chunks == 0) {
         CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
         CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
         m->dev.val = nullptr; m->dev.col = nullptr;
@@ -512,12 +537,13 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
 
     /* kernel choice from the histogram */
     kernel = kernel_from_env(kernel);
-    if (kernel == B200_KERNEL_MERGE) kernel = B200_KERNEL_ORDERED;
     if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL) {
         if (build_panel_locked(m, kernel == B200_KERNEL_PANEL)) kernel = B200_KERNEL_PANEL;
         else kernel = B200_KERNEL_SELL;
     }
-    if (kernel == B200_KERNEL_SELL && !build_sell_locked(m, rowstr)) kernel = B200_KERNEL_ORDERED;
+    if ((kernel == B200_KERNEL_SELL || kernel == B200_KERNEL_MERGE) &&
+        !build_sell_locked(m, rowstr, kernel == B200_KERNEL_MERGE))
+        kernel = B200_KERNEL_ORDERED;
     m->kernel = kernel;
     {
         const double mean = rows > 0 ? (double)nnz / rows : 0.0;
@@ -532,7 +558,7 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
                 b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.padded,
-                m->sell.R, m->sell.G, m->sell.padded, m->sell.n_long_warp, m->sell.n_long);
+                m->sell.R, m->sell.G, m->sell.padded, m->sell.n_long, m->sell.n_chunks);
     return m;
 }
 
@@ -541,7 +567,8 @@ static void release_locked(b200_matrix *m)
     if (!m) return;
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
     cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
-    cudaFree(m->d_scol); cudaFree(m->d_long_rows);
+    cudaFree(m->d_scol); cudaFree(m->d_chunks); cudaFree(m->d_multi); cudaFree(m->d_multi_rows);
+    cudaFree(m->d_carry);
     if (m->d_x) cudaFree(m->d_x);
     if (m->d_y) cudaFree(m->d_y);
     if (m->h_x) cudaFreeHost(m->h_x);
@@ -558,12 +585,12 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else
             launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s);
-    } else if (m->kernel == B200_KERNEL_SELL) {
+    } else if (m->kernel == B200_KERNEL_SELL || m->kernel == B200_KERNEL_MERGE) {
         if (m->dtype == B200_F64)
             launch_sell<double>(m->sell, m->dev, (const double *)d_x, (double *)d_y, s);
         else
             launch_sell<float>(m->sell, m->dev, (const float *)d_x, (float *)d_y, s);
-        launched_kernels = 1 + (m->sell.n_long_warp > 0) + (m->sell.n_long > m->sell.n_long_warp);
+        launched_kernels = 1 + (m->sell.n_chunks > 0) + (m->sell.n_multi > 0);
     } else if (m->dtype == B200_F64) {
         if (m->kernel == B200_KERNEL_VECTOR)
             launch_vector<double>(m->dev, m->lanes, (const double *)d_x, (double *)d_y, s);
@@ -632,8 +659,8 @@ extern "C" const char *b200_spmv_kernel_name(const b200_matrix *m)
 extern "C" int b200_spmv_launches_per_exec(const b200_matrix *m)
 {
     if (m->rows <= 0) return 0;
-    return m->kernel == B200_KERNEL_SELL
-               ? 1 + (m->sell.n_long_warp > 0) + (m->sell.n_long > m->sell.n_long_warp) : 1;
+    return (m->kernel == B200_KERNEL_SELL || m->kernel == B200_KERNEL_MERGE)
+               ? 1 + (m->sell.n_chunks > 0) + (m->sell.n_multi > 0) : 1;
 }
 extern "C" int64_t b200_spmv_algorithmic_bytes(const b200_matrix *m)
 {

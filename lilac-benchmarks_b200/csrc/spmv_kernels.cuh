@@ -103,16 +103,20 @@ struct DevSell {
     const int     *slice_off;  /* int[nblk * R/G/32 + 1] element offsets (multiples of 64) */
     int rows, R, G, nblk, U;
     long long padded;
-    /* rows longer than the cap are left to a CTA-wide (re-ordering) reduction */
-    const int *long_rows;      /* device list of row ids: warp tier first, then CTA tier */
-    int n_long;
-    int n_long_warp;
+    /* rows above the cap: nnz-split chunks + ordered carry fix-up (re-ordering) */
+    const int4 *chunks;        /* {row, lo, hi, carry slot or -1} per chunk */
+    int n_chunks;
+    const int2 *multi;         /* {first carry slot, count} per multi-chunk row */
+    const int  *multi_rows;    /* its row id */
+    int n_multi;
+    void *carry;               /* T[number of carried chunks] */
+    int n_long;                /* rows above the cap */
 };
 void launch_sell_rowlen(const int *rowptr, int rows, int R, int cap, uint16_t *seglen, cudaStream_t s);
 template <typename T>
 void launch_sell_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm,
                       const uint16_t *seglen, T *val_out, int *col_out, cudaStream_t s);
-int sell_warp_row_max();
+int sell_chunk_entries();
 template <typename T>
 void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStream_t s);
 

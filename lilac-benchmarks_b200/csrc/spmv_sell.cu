@@ -221,54 +221,61 @@ spmv_sell_kernel(const T *__restrict__ val, const int *__restrict__ col,
     }
 }
 
-/* long rows, tier 1: one warp per row (cap < len <= kWarpRowMax), tier 2: one
- * CTA per row.  Tree-ordered reductions over the CSR copy. */
-constexpr int kWarpRowMax = 2048;
+/* Long rows (above the cap): nnz-split.  Every long row is cut into chunks of
+ * kChunk entries; one warp reduces one chunk (4 independent loads per lane in
+ * flight, xor-shuffle tree).  A row that fits one chunk is finished there;
+ * otherwise the chunk sums are carried to a fix-up kernel that adds them in
+ * chunk order -- deterministic, no atomics.  This is the load-balanced path
+ * for heavy-tailed row lengths (power-law graphs); it re-orders the sum. */
+constexpr int kChunk = 512;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-spmv_long_rows_warp_kernel(const T *__restrict__ val, const int *__restrict__ col,
-                           const int *__restrict__ rowptr, const int *__restrict__ long_rows,
-                           int n_long, const T *__restrict__ xm1, T *__restrict__ y)
+spmv_long_chunks_kernel(const T *__restrict__ val, const int *__restrict__ col,
+                        const int4 *__restrict__ chunks, int n_chunks,
+                        const T *__restrict__ xm1, T *__restrict__ y, T *__restrict__ carry)
 {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n_long) return;
-    const int r = long_rows[w];
-    const int lo = rowptr[r], hi = rowptr[r + 1];
-    T acc = (T)0;
-    for (int i = lo + lane; i < hi; i += 32)
-        acc = sadd(acc, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
+    if (w >= n_chunks) return;
+    const int4 c = chunks[w];                  /* {row, lo, hi, carry slot or -1} */
+    T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
+    int i = c.y + lane;
+    for (; i + 96 < c.z; i += 128) {
+        const T v0 = __ldcs(val + i), v1 = __ldcs(val + i + 32), v2 = __ldcs(val + i + 64),
+                v3 = __ldcs(val + i + 96);
+        const int c0 = __ldcs(col + i), c1 = __ldcs(col + i + 32), c2 = __ldcs(col + i + 64),
+                  c3 = __ldcs(col + i + 96);
+        a0 = sadd(a0, smul(v0, __ldg(xm1 + c0)));
+        a1 = sadd(a1, smul(v1, __ldg(xm1 + c1)));
+        a2 = sadd(a2, smul(v2, __ldg(xm1 + c2)));
+        a3 = sadd(a3, smul(v3, __ldg(xm1 + c3)));
+    }
+    for (; i < c.z; i += 32) a0 = sadd(a0, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
+    T acc = sadd(sadd(a0, a1), sadd(a2, a3));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-    if (lane == 0) y[r] = acc;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-spmv_long_rows_kernel(const T *__restrict__ val, const int *__restrict__ col,
-                      const int *__restrict__ rowptr, const int *__restrict__ long_rows,
-                      const T *__restrict__ xm1, T *__restrict__ y)
-{
-    __shared__ T red[8];
-    const int r = long_rows[blockIdx.x];
-    const int lo = rowptr[r], hi = rowptr[r + 1];
-    T acc = (T)0;
-    for (int i = lo + threadIdx.x; i < hi; i += 256)
-        acc = sadd(acc, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T s = (T)0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s = sadd(s, red[w]);
-        y[r] = s;
+    if (lane == 0) {
+        if (c.w < 0) y[c.x] = acc;
+        else carry[c.w] = acc;
     }
 }
 
-int sell_warp_row_max() { return kWarpRowMax; }
+/* one thread per multi-chunk row: y[row] = carry[first] + carry[first+1] + ... */
+template <typename T>
+__global__ void spmv_long_fixup_kernel(const int2 *__restrict__ multi, int n_multi,
+                                       const int *__restrict__ rows, const T *__restrict__ carry,
+                                       T *__restrict__ y)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_multi) return;
+    const int2 m = multi[t];                   /* {first carry slot, count} */
+    T acc = (T)0;
+    for (int k = 0; k < m.y; ++k) acc = sadd(acc, carry[m.x + k]);
+    y[rows[t]] = acc;
+}
+
+int sell_chunk_entries() { return kChunk; }
 
 template <typename T, int U>
 static void launch_sell_u(const DevSell &sm, const T *x, T *y, cudaStream_t s)
@@ -285,15 +292,13 @@ void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStr
         else if (sm.U <= 2) launch_sell_u<T, 2>(sm, x, y, s);
         else launch_sell_u<T, 4>(sm, x, y, s);
     }
-    /* long_rows = [n_long_warp rows for the warp tier][the rest for the CTA tier] */
-    if (sm.n_long_warp > 0)
-        spmv_long_rows_warp_kernel<T><<<(sm.n_long_warp + 7) / 8, 256, 0, s>>>(
-            static_cast<const T *>(csr.val), csr.col, csr.rowptr, sm.long_rows, sm.n_long_warp,
-            x - 1, y);
-    if (sm.n_long > sm.n_long_warp)
-        spmv_long_rows_kernel<T><<<sm.n_long - sm.n_long_warp, 256, 0, s>>>(
-            static_cast<const T *>(csr.val), csr.col, csr.rowptr, sm.long_rows + sm.n_long_warp,
-            x - 1, y);
+    if (sm.n_chunks > 0)
+        spmv_long_chunks_kernel<T><<<(sm.n_chunks + 7) / 8, 256, 0, s>>>(
+            static_cast<const T *>(csr.val), csr.col, sm.chunks, sm.n_chunks, x - 1, y,
+            static_cast<T *>(sm.carry));
+    if (sm.n_multi > 0)
+        spmv_long_fixup_kernel<T><<<(sm.n_multi + 255) / 256, 256, 0, s>>>(
+            sm.multi, sm.n_multi, sm.multi_rows, static_cast<const T *>(sm.carry), y);
 }
 template void launch_sell<double>(const DevSell &, const DevCsr &, const double *, double *, cudaStream_t);
 template void launch_sell<float>(const DevSell &, const DevCsr &, const float *, float *, cudaStream_t);

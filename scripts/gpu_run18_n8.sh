@@ -1,0 +1,6 @@
+set -x
+nvidia-smi topo -m 2>/dev/null | head -12
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+echo rc=$?
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_n8.json').read().strip().splitlines()[-1]); print(json.dumps({k:d.get(k) for k in ('value','ms_per_step','roofline','e2e','npb_cg_device_resident')}, indent=1))"; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_n8.err | tail -12

@@ -174,7 +174,7 @@ def test_sell_long_rows_go_to_the_cta_reduction(libspmv, oracle):
     lens[long_ids] = rng.integers(300, 70000, 25)
     a, c, rowstr, x = make_csr(rng, n, 200000, lens, positive=True, sort=False)
     m, y = _exec_resident(libspmv, a, x, rowstr, c, "auto")
-    assert m.kernel_name == "sell" and m.launches_per_exec == 3
+    assert m.kernel_name == "sell" and m.launches_per_exec == 3     # tiles + chunks + carry fix-up
     y0 = oracle.spmv(a, x, rowstr, c)
     is_long = np.zeros(n, dtype=bool)
     is_long[long_ids] = True
@@ -386,3 +386,26 @@ def test_peer_memory_cg_single_rank_group(libspmv, npb, npb_history, cls):
     assert cg.spmv_count == 26 * m.cls.niter
     gold = np.array([float(z) for z in npb_history["classes"][cls]["zeta"]])
     assert np.allclose(zeta, gold, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_merge_kernel_nnz_split_with_carry_fixup(libspmv, oracle, dtype):
+    """B200_KERNEL_MERGE: every row goes through the nnz-split chunks (one warp
+    per 512 entries) and multi-chunk rows are finished by the ordered carry
+    fix-up.  Re-ordered sum: 1e-12 relative on non-cancelling fp64 input,
+    deterministic run to run."""
+    import torch
+    rng = np.random.default_rng(99)
+    n = 3000
+    lens = rng.poisson(8, n)
+    lens[rng.choice(n, 40, replace=False)] = rng.integers(500, 40000, 40)
+    lens[rng.random(n) < 0.05] = 0
+    a, c, rowstr, x = make_csr(rng, n, 100000, lens, dtype=dtype, positive=True, sort=False)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "merge")
+    assert m.kernel_name == "merge" and m.launches_per_exec == 3
+    y0 = oracle.spmv(a, x, rowstr, c)
+    tol = REL_TOL_F64 if dtype == np.float64 else 2e-5
+    nz = y0 != 0
+    assert np.all(np.abs(y - y0)[nz] <= tol * np.abs(y0)[nz]) and np.all(y[~nz] == 0)
+    _, y2 = _exec_resident(libspmv, a, x, rowstr, c, "merge")
+    assert np.array_equal(y, y2)
