@@ -360,8 +360,15 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     const int gran = 32 * G;
     R = std::max(gran, std::min(256 * G, (R + gran - 1) / gran * gran));
     const double mean = (double)m->nnz / m->rows;
+    /* cap: rows above it leave the tiles for the nnz-split path.  A narrow
+     * length distribution (NPB, crsmat: max <= 4 x mean) keeps every row in the
+     * tiles; a heavy tail is cut at ~2.5 x mean, because one long row pads its
+     * whole 32-lane slice (profiles/r01_run19_sweep_merge.txt). */
     int cap = env_int("B200_SPMV_SELL_CAP", 0);
-    if (cap <= 0) cap = (int)std::min(65534.0, std::max(64.0, 4.0 * mean));
+    if (cap <= 0) {
+        if ((double)m->scan.max_len <= 4.0 * std::max(mean, 8.0)) cap = m->scan.max_len;
+        else cap = (int)std::max(32.0, 2.5 * mean);
+    }
     cap = std::min(cap, 65534);
     if (all_rows_split) cap = 0;            /* MERGE: every row goes through the nnz-split path */
     const int nblk = (m->rows + R - 1) / R;
