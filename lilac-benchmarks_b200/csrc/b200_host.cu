@@ -30,11 +30,14 @@
 #include <cuda_runtime.h>
 
 #include <pthread.h>
+#include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <vector>
@@ -111,6 +114,7 @@ struct CacheEntry {
     uint64_t fingerprint;
     uint64_t last_use;
     b200_matrix *m;
+    int guard_slot;            /* index into g_guards, -1 when unguarded */
 };
 
 struct PinnedRange { char *lo, *hi; bool ours; };
@@ -127,6 +131,103 @@ static uint64_t g_tick = 0;
 static b200_spmv_stats g_stats;
 static int g_validate = 0, g_verbose = 0, g_cache_cap = 4, g_time_kernels = 1;
 static int g_zero_copy = 1, g_auto_pin = 0;
+
+/* ------------------------------------------------------------------------
+ * Opt-in write guard (B200_SPMV_GUARD=1): the reference's cache-coherence
+ * device (libspmv/gpu.c:140-209, ALIGN macro :204-209): the host pages of a
+ * resident matrix are made read-only and a SIGSEGV handler invalidates the
+ * cache entry when the caller writes to them, chaining to any handler that was
+ * installed before (gpu.c:180-181).  Differences: only pages lying entirely
+ * inside an array are protected (gpu.c rounds outwards, so a write to a
+ * neighbouring variable on a shared page silently drops the protection -- in
+ * NPB `x` follows `a` in COMMON), and several matrices can be guarded.
+ * The handler only touches this fixed table (async-signal-safe).
+ * ---------------------------------------------------------------------- */
+struct GuardRange { char *lo, *hi; };
+struct GuardSlot {
+    volatile int used;         /* 1 while a cache entry owns the slot */
+    volatile int tripped;      /* set by the handler: host copy was written */
+    GuardRange r[3];
+};
+static const int kMaxGuards = 16;
+static GuardSlot g_guards[kMaxGuards];
+static struct sigaction g_old_segv;
+static bool g_guard_installed = false;
+static int g_guard = 0;
+
+static void guard_handler(int sig, siginfo_t *si, void *ctx)
+{
+    char *addr = (char *)si->si_addr;
+    for (int k = 0; k < kMaxGuards; ++k) {
+        GuardSlot &g = g_guards[k];
+        if (!g.used) continue;
+        for (int j = 0; j < 3; ++j) {
+            if (g.r[j].lo && addr >= g.r[j].lo && addr < g.r[j].hi) {
+                for (int q = 0; q < 3; ++q)
+                    if (g.r[q].lo && g.r[q].hi > g.r[q].lo)
+                        mprotect(g.r[q].lo, (size_t)(g.r[q].hi - g.r[q].lo), PROT_READ | PROT_WRITE);
+                g.tripped = 1;
+                return;                           /* the faulting store is retried */
+            }
+        }
+    }
+    /* not ours: chain (gpu.c:180-181) or fall back to the default action */
+    if ((g_old_segv.sa_flags & SA_SIGINFO) && g_old_segv.sa_sigaction) {
+        g_old_segv.sa_sigaction(sig, si, ctx);
+    } else if (g_old_segv.sa_handler != SIG_DFL && g_old_segv.sa_handler != SIG_IGN &&
+               g_old_segv.sa_handler) {
+        g_old_segv.sa_handler(sig);
+    } else {
+        signal(SIGSEGV, SIG_DFL);
+    }
+}
+
+static GuardRange inner_pages(const void *p, size_t bytes)
+{
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGE_SIZE);
+    uintptr_t lo = ((uintptr_t)p + page - 1) / page * page;
+    uintptr_t hi = ((uintptr_t)p + bytes) / page * page;
+    GuardRange r = {nullptr, nullptr};
+    if (hi > lo) { r.lo = (char *)lo; r.hi = (char *)hi; }
+    return r;
+}
+
+static int guard_arm(const void *a, size_t a_bytes, const int *rowstr, size_t r_bytes,
+                     const int *colidx, size_t c_bytes)
+{
+    if (!g_guard) return -1;
+    if (!g_guard_installed) {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof sa);
+        sa.sa_flags = SA_SIGINFO;
+        sigemptyset(&sa.sa_mask);
+        sa.sa_sigaction = guard_handler;
+        if (sigaction(SIGSEGV, &sa, &g_old_segv) != 0) return -1;
+        g_guard_installed = true;
+    }
+    for (int k = 0; k < kMaxGuards; ++k) {
+        GuardSlot &g = g_guards[k];
+        if (g.used) continue;
+        g.r[0] = inner_pages(a, a_bytes);
+        g.r[1] = inner_pages(rowstr, r_bytes);
+        g.r[2] = inner_pages(colidx, c_bytes);
+        g.tripped = 0;
+        g.used = 1;
+        for (int j = 0; j < 3; ++j)
+            if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ);
+        return k;
+    }
+    return -1;
+}
+
+static void guard_disarm(int slot)
+{
+    if (slot < 0) return;
+    GuardSlot &g = g_guards[slot];
+    for (int j = 0; j < 3; ++j)
+        if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ | PROT_WRITE);
+    g.used = 0;
+}
 
 static void dump_stats_at_exit(void)
 {
@@ -160,6 +261,7 @@ static void ensure_init_locked(int device)
     g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
     g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
     g_auto_pin = env_int("B200_SPMV_PIN_HOST", 0);
+    g_guard = env_int("B200_SPMV_GUARD", 0);
     memset(&g_stats, 0, sizeof g_stats);
     atexit(dump_stats_at_exit);
     g_ready = true;
@@ -763,9 +865,11 @@ static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *c
     for (CacheEntry &e : g_cache) {
         if (e.a == a && e.rowstr == rowstr && e.colidx == colidx && e.rows == rows &&
             e.nnz == nnz && e.dtype == dtype) {
-            if (g_validate &&
-                fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) != e.fingerprint) {
+            const bool tripped = e.guard_slot >= 0 && g_guards[e.guard_slot].tripped;
+            if (tripped || (g_validate &&
+                fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) != e.fingerprint)) {
                 if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
+                guard_disarm(e.guard_slot);
                 release_locked(e.m);
                 e = g_cache.back();
                 g_cache.pop_back();
@@ -781,6 +885,7 @@ static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *c
         size_t victim = 0;
         for (size_t i = 1; i < g_cache.size(); ++i)
             if (g_cache[i].last_use < g_cache[victim].last_use) victim = i;
+        guard_disarm(g_cache[victim].guard_slot);
         release_locked(g_cache[victim].m);
         g_cache[victim] = g_cache.back();
         g_cache.pop_back();
@@ -798,6 +903,9 @@ static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *c
     CUDA_OK(cudaMalloc(&m->d_y, m->y_bytes));
     CUDA_OK(cudaMallocHost(&m->h_x, m->x_bytes));
     CUDA_OK(cudaMallocHost(&m->h_y, m->y_bytes));
+    e.guard_slot = guard_arm(a, (size_t)(rows > 0 ? rowstr[rows] - 1 : 0) * elem_size(dtype), rowstr,
+                             ((size_t)rows + 1) * sizeof(int), colidx,
+                             (size_t)(rows > 0 ? rowstr[rows] - 1 : 0) * sizeof(int));
     g_cache.push_back(e);
     g_stats.uploads++;
     g_stats.upload_ms += now_ms() - t0;
@@ -879,7 +987,7 @@ extern "C" void *f_spmv_harness_(float *ov, float *a, float *iv, int *rowstr, in
 extern "C" void b200_spmv_invalidate(void)
 {
     pthread_mutex_lock(&g_lock);
-    for (CacheEntry &e : g_cache) release_locked(e.m);
+    for (CacheEntry &e : g_cache) { guard_disarm(e.guard_slot); release_locked(e.m); }
     g_cache.clear();
     pthread_mutex_unlock(&g_lock);
 }

@@ -409,3 +409,53 @@ def test_merge_kernel_nnz_split_with_carry_fixup(libspmv, oracle, dtype):
     assert np.all(np.abs(y - y0)[nz] <= tol * np.abs(y0)[nz]) and np.all(y[~nz] == 0)
     _, y2 = _exec_resident(libspmv, a, x, rowstr, c, "merge")
     assert np.array_equal(y, y2)
+
+
+GUARD_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+from lilac_benchmarks_b200 import libspmv
+rng = np.random.default_rng(4)
+n, ncols = 6000, 5000
+lens = rng.poisson(40, n)
+rowstr = np.empty(n + 1, dtype=np.int32); rowstr[0] = 1; rowstr[1:] = 1 + np.cumsum(lens)
+nnz = int(lens.sum())
+colidx = rng.integers(1, ncols + 1, nnz).astype(np.int32)
+a = rng.standard_normal(nnz)
+x = rng.standard_normal(ncols)
+y = np.zeros(n)
+libspmv.spmv_harness(y, a, x, rowstr, colidx, n)
+assert np.array_equal(y, oracle.spmv(a, x, rowstr, colidx))
+libspmv.spmv_harness(y, a, x, rowstr, colidx, n)
+assert libspmv.stats()["uploads"] == 1
+a[nnz // 2] = 123.0            # lands on a protected page: SIGSEGV -> handler -> cache entry stale
+colidx[nnz // 3] = 1
+libspmv.spmv_harness(y, a, x, rowstr, colidx, n)
+assert libspmv.stats()["uploads"] == 2, libspmv.stats()
+assert np.array_equal(y, oracle.spmv(a, x, rowstr, colidx))
+a[nnz // 4] = -1.0             # protection is re-armed after the re-upload (an interior page)
+libspmv.spmv_harness(y, a, x, rowstr, colidx, n)
+assert libspmv.stats()["uploads"] == 3
+assert np.array_equal(y, oracle.spmv(a, x, rowstr, colidx))
+print("guard ok")
+"""
+
+
+def test_write_guard_invalidates_the_resident_matrix(tmp_path):
+    """B200_SPMV_GUARD=1: the opt-in mprotect/SIGSEGV coherence device of
+    libspmv/gpu.c:140-262 -- a host write to a resident matrix marks the cache
+    entry stale (fingerprint check switched off to isolate the guard)."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "guard.py"
+    script.write_text(GUARD_SCRIPT.format(root=root))
+    env = dict(os.environ, B200_SPMV_GUARD="1", B200_SPMV_VALIDATE="0")
+    proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "guard ok" in proc.stdout, proc.stdout
