@@ -502,7 +502,13 @@ template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
-    if (pm.U >= 5) {
+    const int threads = pm.R / pm.G;
+    if (threads <= 256 && pm.U >= 5) {
+        /* few warps per SM (NPB class A / B sized row blocks): the register file
+         * is free, so each lane keeps twice as many pairs of the stream in flight */
+        if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, s);
+        else launch_panel_cfg<T, 8, 256>(pm, x, y, s);     /* best on class B (profiles/r01_run23) */
+    } else if (pm.U >= 5) {
         launch_panel_cfg<T, 5, 512>(pm, x, y, s);
     } else if (pm.U == 3) {
         launch_panel_cfg<T, 3, 512>(pm, x, y, s);
