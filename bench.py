@@ -199,6 +199,10 @@ def run_reference_arm(args, world, rank):
 # --------------------------------------------------------------------------
 def run_b200(args, world, rank, local_rank):
     import torch
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the matrix generator (callers lib, loaded
+        # below) may use this rank's share of the host cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_cores() // world))
     entry.load_package()
     from lilac_benchmarks_b200 import libspmv, npb, sharded
 
@@ -240,7 +244,7 @@ def run_b200(args, world, rank, local_rank):
         layout = sharded.ShardLayout.build(cls.na, world)
         lo, hi = layout.local_range(rank)
         t0 = time.perf_counter()
-        m = npb.NpbMatrix(workload, lo, hi)
+        m = npb.NpbMatrix(workload, lo, hi, pieces=args.pieces)
         t_gen = time.perf_counter() - t0
         t0 = time.perf_counter()
         rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=args.kernel)
@@ -461,6 +465,8 @@ def main():
     ap.add_argument("--no-npb", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=120)
+    ap.add_argument("--pieces", type=int, default=8,
+                    help="N>1: build each rank's row block in this many pieces (bounds host memory)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

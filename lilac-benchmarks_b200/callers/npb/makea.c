@@ -108,28 +108,28 @@ void npb_csr_free(npb_csr *m)
     memset(m, 0, sizeof *m);
 }
 
-int npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out)
-{
-    const int n = c->na, nonzer = c->nonzer, ld = nonzer + 1;
-    const int nrows = row_hi - row_lo;
-    memset(out, 0, sizeof *out);
-    if (row_lo < 0 || row_hi > n || nrows < 0) return -2;
+/* The n generating sparse vectors (cg.f:709-718).  They depend only on the
+ * class, so a process that builds several row blocks keeps them. */
+typedef struct { int n, ld; int *arow, *acol; double *aelt; } npb_vectors;
+static npb_vectors g_vec;     /* cache of the last class generated */
+static char g_vec_cls;
 
+static int make_vectors(const npb_cg_class *c)
+{
+    if (g_vec.arow && g_vec_cls == c->cls && g_vec.n == c->na) return 0;
+    free(g_vec.arow); free(g_vec.acol); free(g_vec.aelt);
+    memset(&g_vec, 0, sizeof g_vec);
+    const int n = c->na, nonzer = c->nonzer, ld = nonzer + 1;
     /* nn1: smallest power of two not less than n (cg.f:700-704) */
     int nn1 = 1;
     do { nn1 *= 2; } while (nn1 < n);
-
     /* random stream: cg.f:186-188 (one draw is consumed before makea) */
     urando_t u = {314159265.0, 1220703125.0};
     (void)npb_randlc(&u.tran, u.amult);
-
     int    *arow = (int *)malloc(sizeof(int) * (size_t)n);
     int    *acol = (int *)malloc(sizeof(int) * (size_t)n * ld);
     double *aelt = (double *)malloc(sizeof(double) * (size_t)n * ld);
-    int64_t *start = (int64_t *)calloc((size_t)nrows + 1, sizeof(int64_t));
-    if (!arow || !acol || !aelt || !start) return -3;
-
-    /* cg.f:709-718 */
+    if (!arow || !acol || !aelt) { free(arow); free(acol); free(aelt); return -3; }
     for (int iouter = 1; iouter <= n; ++iouter) {
         int nzv = nonzer;
         int    *ivc = acol + (size_t)(iouter - 1) * ld;
@@ -138,6 +138,29 @@ int npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out)
         vecset(vc, ivc, &nzv, iouter, 0.5);
         arow[iouter - 1] = nzv;
     }
+    g_vec.n = n; g_vec.ld = ld; g_vec.arow = arow; g_vec.acol = acol; g_vec.aelt = aelt;
+    g_vec_cls = c->cls;
+    return 0;
+}
+
+void npb_makea_release_cache(void)
+{
+    free(g_vec.arow); free(g_vec.acol); free(g_vec.aelt);
+    memset(&g_vec, 0, sizeof g_vec);
+    g_vec_cls = 0;
+}
+
+int npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out)
+{
+    const int n = c->na, ld = c->nonzer + 1;
+    const int nrows = row_hi - row_lo;
+    memset(out, 0, sizeof *out);
+    if (row_lo < 0 || row_hi > n || nrows < 0) return -2;
+    if (make_vectors(c)) return -3;
+    const int *arow = g_vec.arow, *acol = g_vec.acol;
+    const double *aelt = g_vec.aelt;
+    int64_t *start = (int64_t *)calloc((size_t)nrows + 1, sizeof(int64_t));
+    if (!start) return -3;
 
     /* count the triples that land in each kept row (cg.f:778-790) */
     for (int i = 0; i < n; ++i)
@@ -180,7 +203,7 @@ int npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out)
         }
         size = size * ratio;
     }
-    free(arow); free(acol); free(aelt); free(fill);
+    free(fill);
 
     /* sort each row's triples by (column, arrival) and count distinct columns */
     int *rowstr = (int *)malloc(sizeof(int) * ((size_t)nrows + 1));

@@ -49,6 +49,9 @@ void npb_csr_free(npb_csr *m);
  * keeps only rows [row_lo, row_hi) (0-based, half-open).  rowstr is local
  * (row_hi-row_lo+1 entries, starting at 1), colidx stays global. */
 int  npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out);
+/* the generating vectors of the last class are cached between calls (several
+ * row blocks of one class replay the random stream once); this drops them */
+void npb_makea_release_cache(void);
 
 typedef struct {
     double zeta;            /* final zeta */

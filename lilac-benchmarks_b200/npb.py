@@ -43,6 +43,8 @@ def lib():
         L.npb_makea.restype = c_int
         L.npb_makea_rows.argtypes = [POINTER(CgClass), c_int, c_int, POINTER(Csr)]
         L.npb_makea_rows.restype = c_int
+        L.npb_makea_release_cache.argtypes = []
+        L.npb_makea_release_cache.restype = None
         L.npb_csr_free.argtypes = [POINTER(Csr)]
         L.npb_csr_free.restype = None
         L.npb_cg_run.argtypes = [POINTER(CgClass), POINTER(Csr), c_void_p, POINTER(CgResult), c_int]
@@ -63,22 +65,47 @@ def cg_class(letter):
 class NpbMatrix:
     """1-based CSR of one NPB CG class (or a row block of it) as numpy arrays."""
 
-    def __init__(self, letter, row_lo=None, row_hi=None):
+    def __init__(self, letter, row_lo=None, row_hi=None, pieces=1):
+        """`pieces` > 1 builds the block in that many consecutive row ranges to
+        bound the generator's temporary memory (class D/E shards)."""
         self.cls = cg_class(letter)
-        csr = Csr()
         if row_lo is None:
-            rc = lib().npb_makea(C.byref(self.cls), C.byref(csr))
-        else:
-            rc = lib().npb_makea_rows(C.byref(self.cls), int(row_lo), int(row_hi), C.byref(csr))
-        if rc != 0:
-            raise RuntimeError(f"npb_makea failed with {rc}")
-        self.n = csr.n
-        self.nnz = csr.nnz
-        # copy out into numpy-owned memory, then free the C arrays
-        self.rowstr = np.ctypeslib.as_array(csr.rowstr, shape=(csr.n + 1,)).copy()
-        self.colidx = np.ctypeslib.as_array(csr.colidx, shape=(max(csr.nnz, 1),))[:csr.nnz].copy()
-        self.a = np.ctypeslib.as_array(csr.a, shape=(max(csr.nnz, 1),))[:csr.nnz].copy()
-        lib().npb_csr_free(C.byref(csr))
+            row_lo, row_hi = 0, self.cls.na
+        pieces = max(1, min(int(pieces), max(row_hi - row_lo, 1)))
+        cuts = [row_lo + (row_hi - row_lo) * k // pieces for k in range(pieces + 1)]
+        # upper bound of the block's nnz (cg.f: nz = na*(nonzer+1)**2): the pieces are
+        # written straight into preallocated arrays, so no second copy is ever held
+        bound = (row_hi - row_lo) * (self.cls.nonzer + 1) ** 2 if pieces > 1 else 0
+        rowstr = np.empty(row_hi - row_lo + 1, dtype=np.int64)
+        rowstr[0] = 1
+        colidx = np.empty(bound, dtype=np.int32) if pieces > 1 else None
+        a = np.empty(bound, dtype=np.float64) if pieces > 1 else None
+        offset = 0
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            csr = Csr()
+            rc = lib().npb_makea_rows(C.byref(self.cls), int(lo), int(hi), C.byref(csr))
+            if rc != 0:
+                raise RuntimeError(f"npb_makea failed with {rc}")
+            rs = np.ctypeslib.as_array(csr.rowstr, shape=(csr.n + 1,))
+            rowstr[lo - row_lo + 1: hi - row_lo + 1] = rs[1:].astype(np.int64) + offset
+            c_view = np.ctypeslib.as_array(csr.colidx, shape=(max(csr.nnz, 1),))[:csr.nnz]
+            a_view = np.ctypeslib.as_array(csr.a, shape=(max(csr.nnz, 1),))[:csr.nnz]
+            if pieces > 1:
+                colidx[offset: offset + csr.nnz] = c_view
+                a[offset: offset + csr.nnz] = a_view
+            else:
+                colidx, a = c_view.copy(), a_view.copy()     # numpy-owned before the C arrays go
+            offset += int(csr.nnz)
+            lib().npb_csr_free(C.byref(csr))
+        if pieces > 1:
+            lib().npb_makea_release_cache()
+        self.n = row_hi - row_lo
+        self.nnz = offset
+        if offset + 1 > 2 ** 31 - 1:
+            raise RuntimeError("row block exceeds the int32 ABI; use more ranks")
+        self.rowstr = rowstr.astype(np.int32)
+        self.colidx = colidx[:offset]
+        self.a = a[:offset]
 
     def as_csr_struct(self):
         csr = Csr()

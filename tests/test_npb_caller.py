@@ -55,3 +55,11 @@ def test_randlc_first_values(npb):
     # x1 = a*x0 mod 2^46
     expect = (314159265 * 1220703125) % (1 << 46)
     assert x.value == float(expect) and v == expect / float(1 << 46)
+
+
+def test_makea_in_pieces_is_identical(npb):
+    whole = npb.NpbMatrix("W", 1000, 6000)
+    parts = npb.NpbMatrix("W", 1000, 6000, pieces=7)
+    assert parts.n == whole.n and parts.nnz == whole.nnz
+    assert np.array_equal(parts.rowstr, whole.rowstr)
+    assert np.array_equal(parts.colidx, whole.colidx) and np.array_equal(parts.a, whole.a)
