@@ -358,7 +358,7 @@ def run_b200(args, world, rank, local_rank):
                        else "matrix block comparable to L2: HBM fraction may read > 1",
                        "x_vectors_rotated": 4 if world == 1 else 1,
                        "exchange": None if world == 1 else "allgather of x per step (NCCL)",
-                       "same_workload_on_one_gpu": None if world == 1 else {
+                       "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
                            "ms_per_step": 2.7398, "value": 3052.3, "unit": UNIT,
                            "source": "profiles/r01_run20_classD_full_one_gpu.txt (class D, SELL kernel, 1xB200)"},
                        "gen_s": round(t_gen, 2), "upload_s": round(t_upload, 3)},

@@ -533,6 +533,12 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     sm.rows = m->rows; sm.R = R; sm.G = G; sm.nblk = nblk; sm.padded = run;
     sm.U = env_int("B200_SPMV_SELL_U", 2);
     sm.n_long = n_long;
+    /* short single-chunk rows first: they run with 8 lanes per row */
+    const int short_len = sell_short_chunk_entries();
+    auto mid = std::stable_partition(chunks.begin(), chunks.end(), [&](const int4 &c) {
+        return c.w < 0 && c.z - c.y <= short_len;
+    });
+    sm.n_chunks_short = (int)(mid - chunks.begin());
     sm.n_chunks = (int)chunks.size();
     sm.n_multi = (int)multi.size();
     sm.chunks = nullptr; sm.multi = nullptr; sm.multi_rows = nullptr; sm.carry = nullptr;
@@ -699,7 +705,8 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
             launch_sell<double>(m->sell, m->dev, (const double *)d_x, (double *)d_y, s);
         else
             launch_sell<float>(m->sell, m->dev, (const float *)d_x, (float *)d_y, s);
-        launched_kernels = 1 + (m->sell.n_chunks > 0) + (m->sell.n_multi > 0);
+        launched_kernels = 1 + (m->sell.n_chunks_short > 0) +
+                           (m->sell.n_chunks > m->sell.n_chunks_short) + (m->sell.n_multi > 0);
     } else if (m->dtype == B200_F64) {
         if (m->kernel == B200_KERNEL_VECTOR)
             launch_vector<double>(m->dev, m->lanes, (const double *)d_x, (double *)d_y, s);
@@ -769,7 +776,9 @@ extern "C" int b200_spmv_launches_per_exec(const b200_matrix *m)
 {
     if (m->rows <= 0) return 0;
     return (m->kernel == B200_KERNEL_SELL || m->kernel == B200_KERNEL_MERGE)
-               ? 1 + (m->sell.n_chunks > 0) + (m->sell.n_multi > 0) : 1;
+               ? 1 + (m->sell.n_chunks_short > 0) + (m->sell.n_chunks > m->sell.n_chunks_short) +
+                     (m->sell.n_multi > 0)
+               : 1;
 }
 extern "C" int64_t b200_spmv_algorithmic_bytes(const b200_matrix *m)
 {

@@ -104,8 +104,9 @@ struct DevSell {
     int rows, R, G, nblk, U;
     long long padded;
     /* rows above the cap: nnz-split chunks + ordered carry fix-up (re-ordering) */
-    const int4 *chunks;        /* {row, lo, hi, carry slot or -1} per chunk */
+    const int4 *chunks;        /* {row, lo, hi, carry slot or -1} per chunk; short chunks first */
     int n_chunks;
+    int n_chunks_short;        /* chunks of <= sell_short_chunk_entries(): 8 lanes each */
     const int2 *multi;         /* {first carry slot, count} per multi-chunk row */
     const int  *multi_rows;    /* its row id */
     int n_multi;
@@ -117,6 +118,7 @@ template <typename T>
 void launch_sell_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm,
                       const uint16_t *seglen, T *val_out, int *col_out, cudaStream_t s);
 int sell_chunk_entries();
+int sell_short_chunk_entries();
 template <typename T>
 void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStream_t s);
 

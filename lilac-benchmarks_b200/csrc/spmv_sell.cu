@@ -229,33 +229,35 @@ spmv_sell_kernel(const T *__restrict__ val, const int *__restrict__ col,
  * for heavy-tailed row lengths (power-law graphs); it re-orders the sum. */
 constexpr int kChunk = 512;
 
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 spmv_long_chunks_kernel(const T *__restrict__ val, const int *__restrict__ col,
                         const int4 *__restrict__ chunks, int n_chunks,
                         const T *__restrict__ xm1, T *__restrict__ y, T *__restrict__ carry)
 {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= n_chunks) return;
-    const int4 c = chunks[w];                  /* {row, lo, hi, carry slot or -1} */
+    /* V lanes per chunk (adaptive vector-per-row: 8 lanes for chunks of a few
+     * dozen entries, a whole warp otherwise) */
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / V;
+    const int lane = threadIdx.x % V;
+    const bool live = g < n_chunks;
+    const int4 c = live ? chunks[g] : make_int4(0, 0, 0, -1);   /* {row, lo, hi, carry slot or -1} */
     T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
     int i = c.y + lane;
-    for (; i + 96 < c.z; i += 128) {
-        const T v0 = __ldcs(val + i), v1 = __ldcs(val + i + 32), v2 = __ldcs(val + i + 64),
-                v3 = __ldcs(val + i + 96);
-        const int c0 = __ldcs(col + i), c1 = __ldcs(col + i + 32), c2 = __ldcs(col + i + 64),
-                  c3 = __ldcs(col + i + 96);
+    for (; i + 3 * V < c.z; i += 4 * V) {
+        const T v0 = __ldcs(val + i), v1 = __ldcs(val + i + V), v2 = __ldcs(val + i + 2 * V),
+                v3 = __ldcs(val + i + 3 * V);
+        const int c0 = __ldcs(col + i), c1 = __ldcs(col + i + V), c2 = __ldcs(col + i + 2 * V),
+                  c3 = __ldcs(col + i + 3 * V);
         a0 = sadd(a0, smul(v0, __ldg(xm1 + c0)));
         a1 = sadd(a1, smul(v1, __ldg(xm1 + c1)));
         a2 = sadd(a2, smul(v2, __ldg(xm1 + c2)));
         a3 = sadd(a3, smul(v3, __ldg(xm1 + c3)));
     }
-    for (; i < c.z; i += 32) a0 = sadd(a0, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
+    for (; i < c.z; i += V) a0 = sadd(a0, smul(__ldcs(val + i), __ldg(xm1 + __ldcs(col + i))));
     T acc = sadd(sadd(a0, a1), sadd(a2, a3));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-    if (lane == 0) {
+    for (int o = V / 2; o > 0; o >>= 1) acc = sadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (live && lane == 0) {
         if (c.w < 0) y[c.x] = acc;
         else carry[c.w] = acc;
     }
@@ -276,6 +278,7 @@ __global__ void spmv_long_fixup_kernel(const int2 *__restrict__ multi, int n_mul
 }
 
 int sell_chunk_entries() { return kChunk; }
+int sell_short_chunk_entries() { return 96; }
 
 template <typename T, int U>
 static void launch_sell_u(const DevSell &sm, const T *x, T *y, cudaStream_t s)
@@ -292,10 +295,15 @@ void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStr
         else if (sm.U <= 2) launch_sell_u<T, 2>(sm, x, y, s);
         else launch_sell_u<T, 4>(sm, x, y, s);
     }
-    if (sm.n_chunks > 0)
-        spmv_long_chunks_kernel<T><<<(sm.n_chunks + 7) / 8, 256, 0, s>>>(
-            static_cast<const T *>(csr.val), csr.col, sm.chunks, sm.n_chunks, x - 1, y,
+    /* chunks = [n_chunks_short chunks of <= kShortChunk entries][the rest] */
+    if (sm.n_chunks_short > 0)
+        spmv_long_chunks_kernel<T, 8><<<(sm.n_chunks_short + 31) / 32, 256, 0, s>>>(
+            static_cast<const T *>(csr.val), csr.col, sm.chunks, sm.n_chunks_short, x - 1, y,
             static_cast<T *>(sm.carry));
+    if (sm.n_chunks > sm.n_chunks_short)
+        spmv_long_chunks_kernel<T, 32><<<(sm.n_chunks - sm.n_chunks_short + 7) / 8, 256, 0, s>>>(
+            static_cast<const T *>(csr.val), csr.col, sm.chunks + sm.n_chunks_short,
+            sm.n_chunks - sm.n_chunks_short, x - 1, y, static_cast<T *>(sm.carry));
     if (sm.n_multi > 0)
         spmv_long_fixup_kernel<T><<<(sm.n_multi + 255) / 256, 256, 0, s>>>(
             sm.multi, sm.n_multi, sm.multi_rows, static_cast<const T *>(sm.carry), y);
