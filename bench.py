@@ -256,10 +256,14 @@ def run_b200(args, world, rank, local_rank):
         sh = sharded.ShardedSpmv(layout, rank, lambda xf, yl: rm.exec(xf, yl), dist=dist, device=dev)
         x_local = torch.from_numpy(rng.random(hi - lo)).to(dev)
 
+        # headline exchange: this library's own push kernel over NVLink peer memory;
+        # the NCCL allgather variant is timed beside it
+        psh = sharded.PeerShardedSpmv(libspmv, rm, layout, rank, dist=dist, device=dev)
+
         def step(i):
-            sh.step(x_local)
-        launches_per_step = rm.launches_per_exec
-        y = sh.y_local
+            psh.step(x_local)
+        launches_per_step = rm.launches_per_exec + 3       # push, flag wait, product, consumed
+        y = psh.y_local
 
     B = algorithmic_bytes(nnz_global, n_global, ncols)
 
@@ -288,6 +292,20 @@ def run_b200(args, world, rank, local_rank):
         ms = float(t.item())
     sec_per_step = ms / 1e3 / K
     value = B / sec_per_step / 1e9
+    nccl_ms_per_step = None
+    if world > 1:
+        # same step with the NCCL allgather as the exchange
+        for i in range(W):
+            sh.step(x_local)
+        barrier()
+        e0.record()
+        for i in range(K):
+            sh.step(x_local)
+        e1.record()
+        barrier()
+        tn = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        nccl_ms_per_step = float(tn.item()) / K
 
     # ---- end to end through the ABI with host vectors --------------------
     Ke = min(K, 2000)
@@ -357,7 +375,10 @@ def run_b200(args, world, rank, local_rank):
                        "l2_policy": "inputs larger than L2 (no flush)" if B / world > 126e6 * 1.5
                        else "matrix block comparable to L2: HBM fraction may read > 1",
                        "x_vectors_rotated": 4 if world == 1 else 1,
-                       "exchange": None if world == 1 else "allgather of x per step (NCCL)",
+                       "exchange": None if world == 1 else
+                       "x slices pushed into every rank's buffer by this library's kernel over NVLink "
+                       "peer memory (include/b200_peer.h)",
+                       "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                        "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
                            "ms_per_step": 2.7398, "value": 3052.3, "unit": UNIT,
                            "source": "profiles/r01_run20_classD_full_one_gpu.txt (class D, SELL kernel, 1xB200)"},
@@ -365,7 +386,7 @@ def run_b200(args, world, rank, local_rank):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": recorded_traffic(label, rm.kernel_name),
                          "peak_source": peak_src,
-                         "kernel": f"spmv ({rm.kernel_name})" + ("" if world == 1 else " + allgather, per rank")},
+                         "kernel": f"spmv ({rm.kernel_name})" + ("" if world == 1 else " + exchange, per rank")},
             "e2e": {"value": B / e2e_sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3, "steps": Ke,
                     "api": "spmv_harness_ (pinned caller vectors)" if world == 1
@@ -445,6 +466,7 @@ def run_b200(args, world, rank, local_rank):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
+        psh.close()
         dist.barrier()
         dist.destroy_process_group()
 

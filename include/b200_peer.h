@@ -56,6 +56,13 @@ double *b200_peer_xfull(b200_peer_group *g);
 /* copy the local slice v[0..n_local) to offset `lo` of every rank's x buffer,
  * then publish epoch `e` on the vector flag */
 void b200_peer_push(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e, void *stream);
+/* the same, but first wait until every rank has reported (b200_peer_consumed)
+ * that it finished reading vector epoch e_consumed -- for back-to-back
+ * products without a scalar exchange in between */
+void b200_peer_push_after(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
+                          uint64_t e_consumed, void *stream);
+/* report that this rank's product has consumed vector epoch e */
+void b200_peer_consumed(b200_peer_group *g, uint64_t e, void *stream);
 /* block until every rank has published epoch >= e on the vector flag */
 void b200_peer_wait_vector(b200_peer_group *g, uint64_t e, void *stream);
 /* slot <- sum_i x[i]*y[i] (mode 0) or sum_i (x[i]-y[i])^2 (mode 1) of the local

@@ -40,7 +40,8 @@ struct PeerDev {
     double *xfull[NR];
     double *scal[NR];                   /* [B200_PEER_SLOTS][NR] */
     unsigned long long *sflag[NR];      /* [B200_PEER_SLOTS][NR] */
-    unsigned long long *vflag[NR];      /* [NR] */
+    unsigned long long *vflag[NR];      /* [NR] vector published */
+    unsigned long long *rflag[NR];      /* [NR] vector consumed (safe to overwrite) */
     unsigned int *counter;              /* local: last-block detection, one per kernel kind */
     double *partial;                    /* local: kBlocks doubles */
 };
@@ -124,8 +125,11 @@ __device__ __forceinline__ void publish_scalar(const PeerDev &g, int slot, unsig
 }
 
 __global__ void __launch_bounds__(kThreads)
-peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e)
+peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e,
+                 unsigned long long e_consumed)
 {
+    /* do not overwrite a peer's vector before it has finished reading the old one */
+    if (e_consumed) wait_flags(g.rflag[g.rank], g.nranks, e_consumed);
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
@@ -137,6 +141,15 @@ peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
 __global__ void peer_wait_vector_kernel(PeerDev g, unsigned long long e)
 {
     wait_flags(g.vflag[g.rank], g.nranks, e);
+}
+
+/* tell every rank that this rank has finished reading vector epoch e */
+__global__ void peer_consumed_kernel(PeerDev g, unsigned long long e)
+{
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -226,7 +239,8 @@ static size_t seg_x_bytes(int64_t n) { return (((size_t)n + 2) * sizeof(double) 
 static size_t seg_scal_off(int64_t n) { return seg_x_bytes(n); }
 static size_t seg_sflag_off(int64_t n) { return seg_scal_off(n) + B200_PEER_SLOTS * NR * sizeof(double); }
 static size_t seg_vflag_off(int64_t n) { return seg_sflag_off(n) + B200_PEER_SLOTS * NR * sizeof(unsigned long long); }
-static size_t seg_total(int64_t n) { return seg_vflag_off(n) + NR * sizeof(unsigned long long) + 256; }
+static size_t seg_rflag_off(int64_t n) { return seg_vflag_off(n) + NR * sizeof(unsigned long long); }
+static size_t seg_total(int64_t n) { return seg_rflag_off(n) + NR * sizeof(unsigned long long) + 256; }
 
 static void fill_dev(b200_peer_group *g)
 {
@@ -238,6 +252,7 @@ static void fill_dev(b200_peer_group *g)
         d.scal[j] = (double *)(g->peer[j] + seg_scal_off(g->n_global));
         d.sflag[j] = (unsigned long long *)(g->peer[j] + seg_sflag_off(g->n_global));
         d.vflag[j] = (unsigned long long *)(g->peer[j] + seg_vflag_off(g->n_global));
+        d.rflag[j] = (unsigned long long *)(g->peer[j] + seg_rflag_off(g->n_global));
     }
     d.counter = g->counter;
     d.partial = g->partial;
@@ -301,7 +316,19 @@ extern "C" double *b200_peer_xfull(b200_peer_group *g) { return (double *)g->loc
 extern "C" void b200_peer_push(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
                                void *stream)
 {
-    peer_push_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e);
+    peer_push_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e, 0);
+}
+
+extern "C" void b200_peer_push_after(b200_peer_group *g, const double *v, int n_local, int64_t lo,
+                                     uint64_t e, uint64_t e_consumed, void *stream)
+{
+    peer_push_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e,
+                                                                     e_consumed);
+}
+
+extern "C" void b200_peer_consumed(b200_peer_group *g, uint64_t e, void *stream)
+{
+    peer_consumed_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->dev, e);
 }
 
 extern "C" void b200_peer_wait_vector(b200_peer_group *g, uint64_t e, void *stream)

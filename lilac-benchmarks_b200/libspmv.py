@@ -105,6 +105,8 @@ def lib():
     L.b200_peer_xfull.argtypes = [c_void_p]
     L.b200_peer_xfull.restype = c_void_p
     L.b200_peer_push.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, c_void_p]
+    L.b200_peer_push_after.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, u64, c_void_p]
+    L.b200_peer_consumed.argtypes = [c_void_p, u64, c_void_p]
     L.b200_peer_wait_vector.argtypes = [c_void_p, u64, c_void_p]
     L.b200_peer_dot.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, u64, c_void_p]
     L.b200_peer_update_zr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -113,7 +115,7 @@ def lib():
                                      u64, c_void_p]
     L.b200_peer_scale.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, u64, c_void_p]
     L.b200_peer_read_slots.argtypes = [c_void_p, POINTER(c_int), POINTER(u64), c_int, c_void_p, c_void_p]
-    for nm in ("push", "wait_vector", "dot", "update_zr", "update_p", "scale", "read_slots"):
+    for nm in ("push", "push_after", "consumed", "wait_vector", "dot", "update_zr", "update_p", "scale", "read_slots"):
         getattr(L, "b200_peer_" + nm).restype = None
     _lib = L
     return L

@@ -344,3 +344,53 @@ class PeerNpbCg:
         if sync:
             sync()
         return hist_z, hist_r, time.perf_counter() - t0
+
+
+class PeerShardedSpmv:
+    """y_local = A[rows of this rank, :] @ x with the exchange done by this
+    rank's own push kernel over NVLink peer memory (include/b200_peer.h) instead
+    of an NCCL allgather: push my slice into every rank's x buffer, wait for
+    everybody's flag, run the local kernel, report the buffer as consumed."""
+
+    def __init__(self, libspmv_module, resident_matrix, layout, rank, dist=None, device="cuda"):
+        import ctypes as C
+        import torch
+        self.torch = torch
+        self.L = libspmv_module.lib()
+        self.rm, self.layout, self.rank, self.dist = resident_matrix, layout, rank, dist
+        self.lo, self.hi = layout.local_range(rank)
+        world = layout.parts
+        handle = (C.c_ubyte * 64)()
+        self.g = self.L.b200_peer_create(rank, world, layout.rows, handle)
+        if not self.g:
+            raise RuntimeError("b200_peer_create failed")
+        if world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = torch.empty(64 * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine)
+            buf = (C.c_ubyte * (64 * world))(*allh.cpu().tolist())
+            if self.L.b200_peer_connect(self.g, buf) != 0:
+                raise RuntimeError("b200_peer_connect failed")
+            dist.barrier()
+        self.xfull = self.L.b200_peer_xfull(self.g)
+        self.y_local = torch.zeros(self.hi - self.lo, dtype=torch.float64, device=device)
+        self.epoch = 0
+
+    def step(self, x_local):
+        s = self.torch.cuda.current_stream().cuda_stream
+        prev = self.epoch
+        self.epoch += 1
+        self.L.b200_peer_push_after(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo,
+                                    self.epoch, prev, s)
+        self.L.b200_peer_wait_vector(self.g, self.epoch, s)
+        self.rm.exec_ptr(self.xfull, self.y_local.data_ptr(), s)
+        self.L.b200_peer_consumed(self.g, self.epoch, s)
+        return self.y_local
+
+    def close(self):
+        if self.g:
+            self.torch.cuda.synchronize()
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.barrier()
+            self.L.b200_peer_destroy(self.g)
+            self.g = None

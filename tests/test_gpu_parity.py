@@ -459,3 +459,21 @@ def test_write_guard_invalidates_the_resident_matrix(tmp_path):
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0 and "guard ok" in proc.stdout, proc.stdout
+
+
+def test_peer_exchange_spmv_single_rank_group(libspmv, oracle, npb):
+    """PeerShardedSpmv on a group of one: push kernel, publish / consumed
+    flags and the product, three back-to-back steps with changing x."""
+    import torch
+    from lilac_benchmarks_b200 import sharded
+    m = npb.NpbMatrix("W")
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+    sh = sharded.PeerShardedSpmv(libspmv, rm, sharded.ShardLayout.build(m.n, 1), 0)
+    try:
+        rng = np.random.default_rng(8)
+        for _ in range(3):
+            x = rng.standard_normal(m.n)
+            y = sh.step(torch.from_numpy(x).cuda()).cpu().numpy()
+            assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx))
+    finally:
+        sh.close()
