@@ -258,12 +258,25 @@ def run_b200(args, world, rank, local_rank):
 
         # headline exchange: this library's own push kernel over NVLink peer memory;
         # the NCCL allgather variant is timed beside it
-        psh = sharded.PeerShardedSpmv(libspmv, rm, layout, rank, dist=dist, device=dev)
+        try:
+            psh = sharded.PeerShardedSpmv(libspmv, rm, layout, rank, dist=dist, device=dev)
+            ok = 1
+        except Exception as exc:                          # no peer access between the GPUs
+            print(f"bench.py: peer-memory exchange unavailable ({exc}); using the NCCL allgather",
+                  file=sys.stderr)
+            psh, ok = None, 0
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0 and psh is not None:
+            psh.close()
+            psh = None
+        exchange_kind = "peer" if psh is not None else "nccl"
 
         def step(i):
-            psh.step(x_local)
-        launches_per_step = rm.launches_per_exec + 3       # push, flag wait, product, consumed
-        y = psh.y_local
+            (psh or sh).step(x_local)
+        # peer: push, flag wait, product, consumed; nccl: slot copy + product (+ the NCCL kernel)
+        launches_per_step = rm.launches_per_exec + (3 if psh is not None else 1)
+        y = (psh or sh).y_local
 
     B = algorithmic_bytes(nnz_global, n_global, ncols)
 
@@ -376,8 +389,9 @@ def run_b200(args, world, rank, local_rank):
                        else "matrix block comparable to L2: HBM fraction may read > 1",
                        "x_vectors_rotated": 4 if world == 1 else 1,
                        "exchange": None if world == 1 else
-                       "x slices pushed into every rank's buffer by this library's kernel over NVLink "
-                       "peer memory (include/b200_peer.h)",
+                       ("x slices pushed into every rank's buffer by this library's kernel over NVLink "
+                        "peer memory (include/b200_peer.h)" if exchange_kind == "peer"
+                        else "allgather of x per step (NCCL)"),
                        "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                        "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
                            "ms_per_step": 2.7398, "value": 3052.3, "unit": UNIT,
@@ -413,8 +427,11 @@ def run_b200(args, world, rank, local_rank):
                 drv.close()
             return zh, float(tt.item()), count
 
-        zeta_nccl, sec_nccl, _ = run_cg("nccl")
-        zeta_h, cg_sec, spmv_count = run_cg("peer")
+        zeta_nccl, sec_nccl, spmv_count = run_cg("nccl")
+        if exchange_kind == "peer":
+            zeta_h, cg_sec, spmv_count = run_cg("peer")
+        else:
+            zeta_h, cg_sec = zeta_nccl, sec_nccl
 
         class _Cnt:
             pass
@@ -429,7 +446,8 @@ def run_b200(args, world, rank, local_rank):
                 "spmv_launches_per_rank": cg.spmv_count * rm.launches_per_exec,
                 "collectives": cg.collectives,
                 "exchange": "fused into the update / dot kernels over NVLink peer memory "
-                            "(include/b200_peer.h), no NCCL call inside conj_grad",
+                            "(include/b200_peer.h), no NCCL call inside conj_grad"
+                            if exchange_kind == "peer" else "NCCL allgather + allreduce",
                 "nccl_variant": {"time_s": sec_nccl, "zeta": zeta_nccl[-1],
                                  "exchange": "allgather of p + 2 one-scalar allreduces per CG iteration"}}
 
@@ -466,7 +484,8 @@ def run_b200(args, world, rank, local_rank):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
-        psh.close()
+        if psh is not None:
+            psh.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -130,7 +130,16 @@ peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
 {
     /* do not overwrite a peer's vector before it has finished reading the old one */
     if (e_consumed) wait_flags(g.rflag[g.rank], g.nranks, e_consumed);
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    /* 16-byte stores over NVLink when the slice is 16-byte aligned on both sides */
+    const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    const int n2 = vec_ok ? n >> 1 : 0;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v);
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
+        const double2 val = v2[i];
+        for (int j = 0; j < g.nranks; ++j)
+            reinterpret_cast<double2 *>(g.xfull[j] + lo)[i] = val;
+    }
+    for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
     }
@@ -191,10 +200,20 @@ peer_update_p_kernel(PeerDev g, double *p, const double *__restrict__ r, int n, 
 {
     wait_flags(g.sflag[g.rank] + slot_new * NR, g.nranks, e_new);
     const double beta = slot_sum(g, slot_new) / slot_sum(g, slot_old);         /* cg.f:609 */
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const double pi = r[i] + beta * p[i];                                  /* cg.f:614-616 */
+    const bool vec_ok = ((lo & 1) == 0) && (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(r)) & 15) == 0);
+    const int n2 = vec_ok ? n >> 1 : 0;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
+        const double2 rv = reinterpret_cast<const double2 *>(r)[i];
+        double2 pv = reinterpret_cast<double2 *>(p)[i];
+        pv.x = rv.x + beta * pv.x;                                             /* cg.f:614-616 */
+        pv.y = rv.y + beta * pv.y;
+        reinterpret_cast<double2 *>(p)[i] = pv;
+        /* the exchange: every rank's copy of the full vector gets the elements now */
+        for (int j = 0; j < g.nranks; ++j) reinterpret_cast<double2 *>(g.xfull[j] + lo)[i] = pv;
+    }
+    for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double pi = r[i] + beta * p[i];
         p[i] = pi;
-        /* the exchange: every rank's copy of the full vector gets the element now */
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = pi;
     }
     if (last_block(g.counter + 3) && threadIdx.x == 0)
