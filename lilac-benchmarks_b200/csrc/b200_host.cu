@@ -40,6 +40,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 using namespace b200;
@@ -316,6 +317,89 @@ static void build_row_blocks(const int *rowstr, int rows, int tile, std::vector<
  * (row, panel) on average. */
 static const size_t kSmemMax = 227 * 1024;
 
+struct PanelPlan { int P, W, R, G, nbuf, fmt, ring_K, ring_S; };
+
+/* fmt 1 (spmv_panelg.cu): tall row blocks of G * T rows for wide matrices.
+ * One CTA per SM and as few passes over x as the shared-memory budget
+ * (R + 1 running sums) allows; the rest of the 227 KB holds two x slices. */
+static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl, int fmt)
+{
+    if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
+    if (m->scan.rows_unsorted != 0) return false;
+    const size_t es = elem_size(m->dtype);
+    const int kRmax = 4096, kMaxPanels = 512;
+    const int kTmax = fmt == 2 ? std::max(64, std::min(768, env_int("B200_SPMV_PANEL_TMAX", 512))) : 512;
+    int R = env_int("B200_SPMV_PANEL_ROWS", 0);
+    if (R <= 0) {
+        const int passes = (int)((m->rows + (long long)g_sm_count * kRmax - 1) / ((long long)g_sm_count * kRmax));
+        R = (int)((m->rows + (long long)g_sm_count * passes - 1) / ((long long)g_sm_count * passes));
+    }
+    R = std::max(64, std::min(kRmax, R));
+    int G = env_int("B200_SPMV_PANEL_G", 0);
+    if (G != 2 && G != 4 && G != 8) G = R <= 2 * kTmax ? 2 : R <= 4 * kTmax ? 4 : 8;
+    int Tn = (R + G - 1) / G;
+    Tn = std::max(32, std::min(kTmax, (Tn + 31) & ~31));
+    R = Tn * G;
+    const int spb = Tn / 32;
+    int nbuf = env_int("B200_SPMV_PANEL_NBUF", 2) == 1 ? 1 : 2;
+    /* fmt 1: shared memory and L1 share 256 KB per SM, and the matrix stream needs L1 lines
+     * for its loads in flight: leaving the L1 less than ~50 KB costs more than wider panels
+     * gain (class C: 76 us at 202 KB of shared memory, 91 us at 227 KB; profiles/r01_run5_sweep.txt).
+     * fmt 2: the stream lands in a shared-memory ring (S stages of K pair rows per warp),
+     * nothing is left for the L1 to do, so the whole 227 KB is used. */
+    int ring_K = 0, ring_S = 0;
+    size_t ring = 0;
+    size_t budget = std::min<size_t>(kSmemMax, (size_t)env_int("B200_SPMV_PANEL_SMEM_KB", fmt == 2 ? 227 : 200) * 1024);
+    if (fmt == 2) {
+        ring_K = env_int("B200_SPMV_PANEL_RING_K", 4) == 2 ? 2 : 4;
+        const size_t stage = (size_t)spb * ring_K * 32 * (2 * es + 4);
+        /* two stages per warp: a deeper ring takes the room from the x slices, and more,
+         * narrower panels cost more than the extra bytes in flight gain (profiles/r01_run34) */
+        ring_S = std::max(2, std::min(32, env_int("B200_SPMV_PANEL_RING_S", 2)));
+        ring = stage * ring_S + (size_t)spb * ring_S * 8 + 256;
+    }
+    auto width_that_fits = [&](int P) {
+        const size_t table = fmt == 2 ? 0 : ((size_t)P * spb + 1) * 4;
+        const size_t fixed = ((((16 + table + 7) & ~(size_t)7) + (size_t)(R + 1) * es + 15) & ~(size_t)15) + 64 + ring;
+        if (fixed >= budget) return 0;
+        return (int)(std::min<long long>(32736, (long long)((budget - fixed) / (nbuf * es)) - 4) & ~31);
+    };
+    int wmax = env_int("B200_SPMV_PANEL_COLS", 0);
+    int P = 1, W = 0;
+    for (int it = 0; it < 8; ++it) {                 /* P and the slice table size depend on each other */
+        int w = width_that_fits(P);
+        if (wmax > 0) w = std::min(w, wmax & ~31);
+        if (w < 32) return false;
+        const int Pn = (m->ncols + w - 1) / w;
+        W = w;
+        if (Pn <= P) break;
+        P = Pn;
+    }
+    if (P > kMaxPanels || (long long)P * W < m->ncols) return false;
+    W = std::min(W, ((((m->ncols + P - 1) / P) + 31) & ~31));
+    P = (m->ncols + W - 1) / W;                      /* rounding W up may have emptied the last panels */
+    pl->P = P; pl->W = W; pl->R = R; pl->G = G; pl->nbuf = nbuf; pl->fmt = fmt;
+    pl->ring_K = ring_K; pl->ring_S = ring_S;
+    return true;
+}
+
+/* modelled launch time of a ring plan against the SELL family, both fitted on NPB
+ * class D row blocks (profiles/r01_run37_sweep.txt): the ring kernel streams ~4.6 TB/s
+ * of stored entries and pays ~0.65 us per panel (barrier, x slice hand-over) in every
+ * wave of CTAs; SELL is bound by the L1TEX wavefront rate of its gather,
+ * ~1.29 clk per entry and SM. */
+static bool panel_plan_beats_sell(const b200_matrix *m, const PanelPlan &pl)
+{
+    const double es = (double)elem_size(m->dtype);
+    const double nblk = (double)((m->rows + pl.R - 1) / pl.R);
+    const double stream = (double)m->nnz * (es + 2) * 1.09 + (double)m->rows * pl.P * 2;
+    const double waves = std::ceil(nblk / g_sm_count);
+    const double t_panel = waves * (stream / (waves * 4.6e12) * std::max(1.0, waves * g_sm_count / nblk) +
+                                    pl.P * 0.65e-6);
+    const double t_sell = (double)m->nnz * 1.29 / (g_sm_count * 1.965e9);
+    return t_panel < 0.92 * t_sell;
+}
+
 static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out, int *G_out,
                              int *nbuf_out)
 {
@@ -368,15 +452,26 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
 
 static bool build_panel_locked(b200_matrix *m, bool forced)
 {
-    int P, W, R, G, nbuf;
-    if (!panel_applicable(m, &P, &W, &R, &G, &nbuf)) return false;
-    {
+    int P, W, R, G, nbuf, fmt = 0, ring_K = 0, ring_S = 0;
+    const int want_fmt = env_int("B200_SPMV_PANEL_FMT", -1);
+    bool ok = false;
+    if (want_fmt <= 0 && panel_applicable(m, &P, &W, &R, &G, &nbuf)) {
         /* every CTA loads the whole x once: only worth it while that stays below the
          * matrix stream itself (short, wide row blocks fail this: NPB class D shards) */
         const double x_bytes = (double)((m->rows + R - 1) / R) * (double)P * W * elem_size(m->dtype);
         const double a_bytes = (double)m->nnz * (elem_size(m->dtype) + 2);
-        if (!forced && x_bytes > a_bytes) return false;
+        ok = forced || x_bytes <= a_bytes;
     }
+    if (!ok && want_fmt != 0) {
+        /* wide matrices: tall row blocks, G rows per lane (spmv_panelg.cu) */
+        PanelPlan pl;
+        if (panel_plan_flagged(m, &pl, want_fmt == 1 ? 1 : 2) && (forced || panel_plan_beats_sell(m, pl))) {
+            P = pl.P; W = pl.W; R = pl.R; G = pl.G; nbuf = pl.nbuf; fmt = pl.fmt;
+            ring_K = pl.ring_K; ring_S = pl.ring_S;
+            ok = true;
+        }
+    }
+    if (!ok) return false;
     const size_t es = elem_size(m->dtype);
     const int nblk = (m->rows + R - 1) / R;
     const int Tn = R / G;
@@ -391,9 +486,14 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
     launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
-    CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)ntiles * Tn * sizeof(ushort4)));
+    /* fmt 0: one ushort4 per lane and tile; fmt 1: G row ids per lane and tile */
+    const size_t meta_bytes = fmt >= 1 ? (size_t)ntiles * R * sizeof(uint16_t) : (size_t)ntiles * Tn * sizeof(ushort4);
+    CUDA_OK(cudaMalloc((void **)&m->d_meta, meta_bytes));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, g_stream);
+    if (fmt >= 1)
+        launch_panelg_sort(d_seglen, ntiles, R, G, reinterpret_cast<uint16_t *>(m->d_meta), d_cnt, g_stream);
+    else
+        launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, g_stream);
     CUDA_OK(cudaGetLastError());
     int overflow = 0;
     std::vector<int> cnt((size_t)nslices + 1);
@@ -403,7 +503,19 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaFree(d_overflow));
     /* exclusive scan of the padded slice sizes (host; a few 10^4 entries) */
     long long run = 0;
-    for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
+    if (fmt == 2) {
+        /* ring kernel: a warp's slices of all panels back to back -- (row block, warp, panel) */
+        std::vector<int> off((size_t)nslices + 1);
+        for (int rb = 0; rb < nblk; ++rb)
+            for (int w = 0; w < spb; ++w)
+                for (int pp = 0; pp < P; ++pp) {
+                    off[((size_t)rb * spb + w) * P + pp] = (int)std::min<long long>(run, 0x7fffffffLL);
+                    run += cnt[((size_t)rb * P + pp) * spb + w];
+                }
+        cnt.swap(off);
+    } else {
+        for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
+    }
     if (overflow || run > 0x7fffff00LL) {
         CUDA_OK(cudaFree(d_cnt));
         CUDA_OK(cudaFree(d_seglen));
@@ -422,12 +534,21 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
     DevPanel &pm = m->panel;
     pm.val = m->d_pval; pm.col = m->d_pcol; pm.meta = m->d_meta; pm.slice_off = m->d_slice_off;
+    pm.rowids = reinterpret_cast<const uint16_t *>(m->d_meta);
+    pm.fmt = fmt; pm.ring_K = ring_K; pm.ring_S = ring_S;
     pm.rows = m->rows; pm.ncols = m->ncols; pm.R = R; pm.G = G; pm.P = P; pm.W = W; pm.nblk = nblk;
     pm.U = env_int("B200_SPMV_PANEL_U", 5);
     pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
     pm.nbuf = nbuf;
     pm.padded = run;
-    if (m->dtype == B200_F64)
+    if (fmt >= 1) {
+        if (m->dtype == B200_F64)
+            launch_panelg_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
+                                       d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
+        else
+            launch_panelg_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
+                                      d_seglen, (float *)m->d_pval, m->d_pcol, g_stream);
+    } else if (m->dtype == B200_F64)
         launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
                                   d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
     else
@@ -436,13 +557,14 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(g_stream));
     CUDA_OK(cudaFree(d_seglen));
-    if (panel_smem_bytes(pm, m->dtype == B200_F32) > kSmemMax)
+    if ((fmt == 2 ? panelr_smem_bytes(pm, m->dtype == B200_F32) :
+         fmt == 1 ? panelg_smem_bytes(pm, m->dtype == B200_F32) : panel_smem_bytes(pm, m->dtype == B200_F32)) > kSmemMax)
         die("panel shared-memory budget exceeded (W=%d R=%d)", W, R);
     /* the CSR copy of val / col is no longer needed */
     CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
     CUDA_OK(cudaFree(m->d_col)); m->d_col = nullptr;
     m->dev.val = nullptr; m->dev.col = nullptr;
-    m->resident_bytes = (int64_t)(nval * es + nval * 2 + (size_t)ntiles * Tn * 8 + ((size_t)nslices + 1) * 4 +
+    m->resident_bytes = (int64_t)(nval * es + nval * 2 + meta_bytes + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
     return true;
 }
@@ -669,10 +791,10 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     if (g_verbose)
         fprintf(stderr,
                 "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
-                "unsorted_rows=%d blocks=%d kernel=%s panel[R=%d G=%d P=%d W=%d nbuf=%d padded=%lld] sell[R=%d G=%d padded=%lld long=%d/%d]\n",
+                "unsorted_rows=%d blocks=%d kernel=%s panel[fmt=%d R=%d G=%d P=%d W=%d nbuf=%d ring=%dx%d padded=%lld] sell[R=%d G=%d padded=%lld long=%d/%d]\n",
                 dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
-                b200_spmv_kernel_name(m), m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.padded,
+                b200_spmv_kernel_name(m), m->panel.fmt, m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.ring_S, m->panel.ring_K, m->panel.padded,
                 m->sell.R, m->sell.G, m->sell.padded, m->sell.n_long, m->sell.n_chunks);
     return m;
 }
@@ -696,7 +818,17 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
     if (m->rows == 0) return 0;
     int launched_kernels = 1;
     if (m->kernel == B200_KERNEL_PANEL) {
-        if (m->dtype == B200_F64)
+        if (m->panel.fmt == 2) {
+            if (m->dtype == B200_F64)
+                launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, s);
+            else
+                launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+        } else if (m->panel.fmt == 1) {
+            if (m->dtype == B200_F64)
+                launch_panelg<double>(m->panel, (const double *)d_x, (double *)d_y, s);
+            else
+                launch_panelg<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+        } else if (m->dtype == B200_F64)
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else
             launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s);

@@ -1,0 +1,155 @@
+/*
+ * panel_common.cuh -- device primitives shared by the PANEL kernels
+ * (spmv_panel.cu: two rows per lane, paired; spmv_panelg.cu: G rows per lane,
+ * flagged streams): separately rounded multiply / add, mbarrier + TMA bulk
+ * copies, the prefetch chunk and the read cursor over a lane stream.
+ */
+#pragma once
+#include "spmv_kernels.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ double pmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  pmul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ double padd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float  padd(float a, float b)   { return __fadd_rn(a, b); }
+
+template <typename T> struct PairT;
+template <> struct PairT<double> { using type = double2; };
+template <> struct PairT<float>  { using type = float2; };
+
+/* ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) --------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <typename T, int U>
+struct Chunk {
+    typename PairT<T>::type v[U];
+    uint32_t c[U];
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT<T>::type *vp,
+                                           const uint32_t *cp, int kp, int npair)
+{
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (kp + u < npair) {
+            ch.v[u] = __ldcs(vp + (size_t)(kp + u) * 32);
+            ch.c[u] = __ldcs(cp + (size_t)(kp + u) * 32);
+        }
+    }
+}
+
+/* Read cursor over a lane stream: walks the pairs of panel 0, 1, ... of this
+ * warp's slices in chunks of U pairs, so that the matrix stream stays
+ * requested ahead of its use across panel boundaries.  Every panel is walked
+ * in an even number of chunks (consumption alternates two register sets). */
+struct StreamCursor {
+    int p;          /* panel being requested */
+    int kp;         /* next pair inside that panel's slice */
+    int npair;      /* pairs of that slice */
+    int nround;     /* pairs walked for that slice: npair rounded up to 2U */
+    size_t base;    /* pair offset of the slice + lane */
+};
+
+/* position the cursor on the first non-empty slice at or after panel cur.p
+ * (the consumer spends no chunk on an empty slice, so neither may the cursor) */
+template <int U>
+__device__ __forceinline__ void cursor_seek(StreamCursor &cur, const int2 *s_slice, int spb,
+                                            int warp, int lane, int P)
+{
+    while (cur.p < P) {
+        const int2 so = s_slice[cur.p * spb + warp];
+        if (so.y > 0) {
+            cur.kp = 0;
+            cur.npair = so.y;
+            cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
+            cur.base = (size_t)(so.x >> 1) + lane;
+            return;
+        }
+        ++cur.p;
+    }
+}
+
+template <typename T, int U>
+__device__ __forceinline__ void cursor_load(Chunk<T, U> &ch, StreamCursor &cur,
+                                            const typename PairT<T>::type *val2,
+                                            const uint32_t *col2, const int2 *s_slice, int spb,
+                                            int warp, int lane, int P)
+{
+    if (cur.p < P) {
+        load_chunk<T, U>(ch, val2 + cur.base, col2 + cur.base, cur.kp, cur.npair);
+        cur.kp += U;
+        if (cur.kp >= cur.nround) {
+            ++cur.p;
+            cursor_seek<U>(cur, s_slice, spb, warp, lane, P);
+        }
+    }
+}
+
+/* ---- flagged streams (spmv_panelg.cu, spmv_panelr.cu) ---------------------- */
+/* the G row ids of a lane, 16 bits each, consumed front to back */
+template <int G> struct RowIds { uint32_t w[G / 2]; };
+
+template <int G>
+__device__ __forceinline__ RowIds<G> load_ids(const uint16_t *p)
+{
+    RowIds<G> r;
+    if constexpr (G == 2) {
+        r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+    } else if constexpr (G == 4) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        r.w[0] = v.x; r.w[1] = v.y;
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+    }
+    return r;
+}
+
+template <int G>
+__device__ __forceinline__ int pop_id(RowIds<G> &ids)
+{
+    const int r = (int)(ids.w[0] & 0xFFFFu);
+#pragma unroll
+    for (int i = 0; i + 1 < G / 2; ++i) ids.w[i] = __funnelshift_r(ids.w[i], ids.w[i + 1], 16);
+    ids.w[G / 2 - 1] >>= 16;
+    return r;
+}
+
+}  // namespace b200

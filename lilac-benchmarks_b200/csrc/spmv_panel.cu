@@ -40,56 +40,9 @@
  * Algorithmic bytes are unchanged; the private layout streams
  * ~10 B per nonzero plus padding.
  */
-#include "spmv_kernels.cuh"
+#include "panel_common.cuh"
 
 namespace b200 {
-
-__device__ __forceinline__ double pmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float  pmul(float a, float b)   { return __fmul_rn(a, b); }
-__device__ __forceinline__ double padd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float  padd(float a, float b)   { return __fadd_rn(a, b); }
-
-template <typename T> struct PairT;
-template <> struct PairT<double> { using type = double2; };
-template <> struct PairT<float>  { using type = float2; };
-
-/* ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) --------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-/* global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned */
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 
 /* ---- build: entries of every (row, panel) -------------------------------- */
 __global__ void panel_count_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
@@ -259,25 +212,6 @@ template void launch_panel_fill<float>(const float *, const int *, const int *, 
 /* ------------------------------------------------------------------------
  * the product
  * ---------------------------------------------------------------------- */
-template <typename T, int U>
-struct Chunk {
-    typename PairT<T>::type v[U];
-    uint32_t c[U];
-};
-
-template <typename T, int U>
-__device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT<T>::type *vp,
-                                           const uint32_t *cp, int kp, int npair)
-{
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (kp + u < npair) {
-            ch.v[u] = __ldcs(vp + (size_t)(kp + u) * 32);
-            ch.c[u] = __ldcs(cp + (size_t)(kp + u) * 32);
-        }
-    }
-}
-
 /* consume U pairs in order; `sw` is the pair index at which the lane stream
  * moves on to its second row (running sums parked in shared memory) */
 template <typename T, int U>
@@ -305,40 +239,6 @@ __device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T
         }
     }
     return acc;
-}
-
-/* Read cursor over a lane stream: walks the pairs of panel 0, 1, ... of this
- * warp's slices in chunks of U pairs, so that the matrix stream stays
- * requested ahead of its use across panel boundaries.  Every panel is walked
- * in an even number of chunks (consumption alternates two register sets). */
-struct StreamCursor {
-    int p;          /* panel being requested */
-    int kp;         /* next pair inside that panel's slice */
-    int npair;      /* pairs of that slice */
-    int nround;     /* pairs walked for that slice: npair rounded up to 2U */
-    size_t base;    /* pair offset of the slice + lane */
-};
-
-template <typename T, int U>
-__device__ __forceinline__ void cursor_load(Chunk<T, U> &ch, StreamCursor &cur,
-                                            const typename PairT<T>::type *val2,
-                                            const uint32_t *col2, const int2 *s_slice, int spb,
-                                            int warp, int lane, int P)
-{
-    if (cur.p < P) {
-        load_chunk<T, U>(ch, val2 + cur.base, col2 + cur.base, cur.kp, cur.npair);
-        cur.kp += U;
-        if (cur.kp >= cur.nround) {
-            ++cur.p;
-            if (cur.p < P) {
-                const int2 so = s_slice[cur.p * spb + warp];
-                cur.kp = 0;
-                cur.npair = so.y;
-                cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
-                cur.base = (size_t)(so.x >> 1) + lane;
-            }
-        }
-    }
 }
 
 template <typename T, int U, int MAXT>
@@ -423,12 +323,8 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
     /* request the first two chunks of the matrix stream */
     StreamCursor cur;
-    {
-        const int2 so = s_slice[warp];
-        cur.p = 0; cur.kp = 0; cur.npair = so.y;
-        cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
-        cur.base = (size_t)(so.x >> 1) + lane;
-    }
+    cur.p = 0; cur.kp = 0; cur.npair = 0; cur.nround = 0; cur.base = 0;
+    cursor_seek<U>(cur, s_slice, spb, warp, lane, P);
     Chunk<T, U> a, b;
     cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
     cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);

@@ -1,0 +1,304 @@
+/*
+ * spmv_panelr.cu -- PANEL with the matrix stream in a shared-memory ring
+ * ("ring kernel", DevPanel::fmt == 2).
+ *
+ * What limits the register-staged PANEL kernels on wide matrices (NPB class D
+ * row blocks: ~110 panels, ~4 entries per (row, panel)) is how much of the
+ * matrix stream is in flight: a lane holds two chunks of U pairs, every panel
+ * is walked in whole chunks, so with a few pairs per lane and panel the
+ * prefetch reaches one panel ahead (~48 KB per SM), and the loads in flight
+ * also need L1 lines, which the x slices in shared memory take away
+ * (profiles/r01_run28, r01_run29).  Here the stream never touches registers
+ * or L1 on its way in:
+ *
+ *   - the slices are stored warp-major -- (row block, warp, panel) -- so a
+ *     warp's stream over ALL panels of its row block is one contiguous run of
+ *     pair rows (32 lanes x {value pair, column pair});
+ *   - every warp owns a ring of S stages of K pair rows in shared memory and
+ *     refills a stage with two TMA bulk copies (values, columns) as soon as
+ *     it has consumed it; one mbarrier per stage.  Stages ignore panel
+ *     boundaries, so the bytes in flight are the ring size whatever the
+ *     panel geometry;
+ *   - the consumer is the flagged-stream consumer of spmv_panelg.cu: x slice
+ *     of the panel in shared memory (TMA, double-buffered), bit 15 of a
+ *     column starts a new row of the lane, running sums parked in shared
+ *     memory, separately rounded multiply and add in the reference's order
+ *     (libspmv/native-impl.c:1-12) => bit-identical results for sorted rows.
+ */
+#include "panel_common.cuh"
+
+namespace b200 {
+
+/* running-sum state of a lane: the row being accumulated and, already loaded,
+ * the parked sum of the row that comes next -- so a row switch costs a store
+ * and two moves, not a dependent shared-memory round trip */
+template <typename T, int G>
+struct LaneRows {
+    RowIds<G> ids;     /* rows after `nxt`, front to back */
+    int cur, nxt;      /* tile-local row ids (R = dummy slot) */
+    T acc, acc_nxt;
+};
+
+template <typename T, int G>
+__device__ __forceinline__ void switch_row(LaneRows<T, G> &st, T *sums)
+{
+    sums[st.cur] = st.acc;
+    st.cur = st.nxt;
+    st.acc = st.acc_nxt;
+    st.nxt = pop_id<G>(st.ids);
+    st.acc_nxt = sums[st.nxt];        /* rows of a lane are distinct: never the slot just stored */
+}
+
+/* consume n <= K pair rows of one ring stage, rv / rc pointing at the first of them
+ * (FULL: n == K, no per-row predicates).  Row slots are padded to a common length inside
+ * a slice (panelg_sort_kernel), so the flags of the 32 lanes fall on the same pair: one
+ * warp vote per pair keeps the switch code off the common path. */
+template <typename T, int G, int K, bool FULL>
+__device__ __forceinline__ void consume_rows(const typename PairT<T>::type *rv, const uint32_t *rc,
+                                             int n, const T *xs, T *sums, LaneRows<T, G> &st)
+{
+    typename PairT<T>::type v[K];
+    uint32_t c[K];
+    T xa[K], xb[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+        if (FULL || u < n) {
+            v[u] = rv[u * 32];
+            c[u] = rc[u * 32];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+        if (FULL || u < n) {
+            xa[u] = xs[c[u] & 0x7FFFu];
+            xb[u] = xs[(c[u] >> 16) & 0x7FFFu];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+        if (FULL || u < n) {
+            const T p0 = pmul(v[u].x, xa[u]), p1 = pmul(v[u].y, xb[u]);
+            if (__any_sync(0xffffffffu, c[u] & 0x80008000u)) {
+                if (c[u] & 0x8000u) switch_row<T, G>(st, sums);
+                st.acc = padd(st.acc, p0);
+                if (c[u] & 0x80000000u) switch_row<T, G>(st, sums);
+                st.acc = padd(st.acc, p1);
+            } else {
+                st.acc = padd(padd(st.acc, p0), p1);
+            }
+        }
+    }
+}
+
+template <typename T, int G, int K, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
+                   const uint16_t *__restrict__ rowids, const int *__restrict__ slice_off,
+                   const T *__restrict__ x, T *__restrict__ y,
+                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S)
+{
+    using P2 = typename PairT<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Tn = blockDim.x;
+    const int spb = Tn >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rb = blockIdx.x;
+    /* layout: [x mbarriers 16 B][ring mbarriers spb*S*8][sums R+1][xbuf nbuf*(W+pad)][ring values][ring columns] */
+    uint64_t *xbars = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *rbars = reinterpret_cast<uint64_t *>(smem_raw + 16);
+    const size_t soff = 16 + (size_t)spb * S * 8;
+    T *sums = reinterpret_cast<T *>(smem_raw + soff);
+    const size_t xoff = (soff + (size_t)(R + 1) * sizeof(T) + 15) & ~(size_t)15;
+    const int WS = W + (16 / (int)sizeof(T));
+    T *xbuf = reinterpret_cast<T *>(smem_raw + xoff);
+    const size_t roff = (xoff + (size_t)nbuf * WS * sizeof(T) + 127) & ~(size_t)127;
+    P2 *ring_val = reinterpret_cast<P2 *>(smem_raw + roff);
+    uint32_t *ring_col = reinterpret_cast<uint32_t *>(smem_raw + roff + (size_t)spb * S * K * 32 * sizeof(P2));
+
+    for (int i = tid; i <= R; i += Tn) sums[i] = (T)0;
+    if (tid == 0) {
+        xbuf[W] = (T)0;                                   /* padding slot, never overwritten */
+        if (nbuf == 2) xbuf[WS + W] = (T)0;
+        mbar_init(&xbars[0], 1);
+        mbar_init(&xbars[1], 1);
+    }
+    if (lane == 0)
+        for (int s = 0; s < S; ++s) mbar_init(&rbars[warp * S + s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    /* this warp's stream: pair rows [0, total) of 32 lanes x (value pair, column pair) */
+    const int *woff = slice_off + ((size_t)rb * spb + warp) * P;
+    const int off0 = __ldg(woff);
+    const int total = (__ldg(woff + P) - off0) >> 6;
+    const int nstage = (total + K - 1) / K;
+    const P2 *gval = reinterpret_cast<const P2 *>(val) + (off0 >> 1);
+    const uint32_t *gcol = reinterpret_cast<const uint32_t *>(col) + (off0 >> 1);
+    P2 *rv_w = ring_val + (size_t)warp * S * K * 32 + lane;
+    uint32_t *rc_w = ring_col + (size_t)warp * S * K * 32 + lane;
+    uint64_t *rb_w = rbars + warp * S;
+
+    auto issue_stage = [&](int t, int slot) {            /* lane 0: stage t -> slot t % S */
+        const int r0 = t * K;
+        const int nr = min(K, total - r0);
+        const uint32_t bv = (uint32_t)(nr * 32 * sizeof(P2)), bc = (uint32_t)(nr * 32 * 4);
+        uint64_t *bar = rb_w + slot;
+        mbar_expect_tx(bar, bv + bc);
+        tma_bulk_g2s(rv_w - lane + (size_t)slot * K * 32, gval + (size_t)r0 * 32, bv, bar);
+        tma_bulk_g2s(rc_w - lane + (size_t)slot * K * 32, gcol + (size_t)r0 * 32, bc, bar);
+    };
+    if (lane == 0)
+        for (int t = 0; t < S && t < nstage; ++t) issue_stage(t, t);
+
+    auto issue_panel = [&](int p) {                       /* thread 0 only (TMA path) */
+        const int cbase = p * W;
+        const int cw = min(W, ncols - cbase);
+        T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+        constexpr int VE = 16 / sizeof(T);
+        const int cw_al = cw & ~(VE - 1);
+        for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);   /* ragged tail */
+        fence_proxy_async();
+        uint64_t *bar = &xbars[p & (nbuf - 1)];
+        mbar_expect_tx(bar, (uint32_t)(cw_al * sizeof(T)));
+        uint32_t left = (uint32_t)(cw_al * sizeof(T));
+        const char *src = reinterpret_cast<const char *>(x + cbase);
+        char *d = reinterpret_cast<char *>(dst);
+        while (left) {
+            const uint32_t n = left > 32768u ? 32768u : left;
+            tma_bulk_g2s(d, src, n, bar);
+            d += n; src += n; left -= n;
+        }
+    };
+    auto coop_panel = [&](int p) {                        /* all threads (x not 16-byte aligned) */
+        const int cbase = p * W;
+        const int cw = min(W, ncols - cbase);
+        T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+        for (int i = tid; i < cw; i += Tn) dst[i] = __ldg(x + cbase + i);
+    };
+    if (use_tma) {
+        if (tid == 0) issue_panel(0);
+    } else {
+        coop_panel(0);
+    }
+
+    const uint16_t *my_ids = rowids + ((size_t)rb * P * Tn + tid) * G;
+    RowIds<G> ids_next = load_ids<G>(my_ids);
+    int o_cur = off0;
+    int o_nxt = __ldg(woff + 1);
+    int t_cur = 0;          /* stage being consumed */
+    int slot = 0;           /* its ring slot, t_cur % S */
+    uint32_t par = 0;       /* mbarrier phase of that slot, (t_cur / S) & 1 */
+    int sr = 0;             /* pair rows of the stage already consumed */
+
+    for (int p = 0; p < P; ++p) {
+        LaneRows<T, G> st;
+        st.ids = ids_next;
+        if (p + 1 < P) ids_next = load_ids<G>(my_ids + (size_t)(p + 1) * Tn * G);
+        const int npair = (o_nxt - o_cur) >> 6;
+        o_cur = o_nxt;
+        if (p + 1 < P) o_nxt = __ldg(woff + p + 2);
+
+        if (use_tma) {
+            if (tid == 0) {
+                if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
+                if (nbuf == 1 && p > 0) issue_panel(p);
+            }
+            mbar_wait(&xbars[p & (nbuf - 1)], (uint32_t)((p >> (nbuf - 1)) & 1));
+        } else {
+            if (nbuf == 2 && p + 1 < P) coop_panel(p + 1);
+            if (nbuf == 1 && p > 0) coop_panel(p);
+            __syncthreads();
+        }
+        const T *xs = xbuf + (size_t)(p & (nbuf - 1)) * WS;
+
+        /* slot R: dummy "current row" until the first flag.  Once a lane's ids are used up
+         * pop_id returns 0 and the pre-load reads sums[0]: harmless, it is never switched to */
+        st.cur = R;
+        st.acc = (T)0;
+        st.nxt = pop_id<G>(st.ids);
+        st.acc_nxt = sums[st.nxt];
+        int kp = 0;
+        while (kp < npair) {                              /* warp-uniform control flow */
+            if (sr == 0) mbar_wait(rb_w + slot, par);
+            const int n = min(npair - kp, K - sr);
+            const int ro = (slot * K + sr) * 32;
+            if (n == K) consume_rows<T, G, K, true>(rv_w + ro, rc_w + ro, n, xs, sums, st);
+            else        consume_rows<T, G, K, false>(rv_w + ro, rc_w + ro, n, xs, sums, st);
+            kp += n;
+            sr += n;
+            if (sr == K) {                                /* stage consumed: refill its slot */
+                __syncwarp();
+                if (lane == 0 && t_cur + S < nstage) {
+                    fence_proxy_async();
+                    issue_stage(t_cur + S, slot);
+                }
+                ++t_cur;
+                sr = 0;
+                if (++slot == S) { slot = 0; par ^= 1u; }
+            }
+        }
+        sums[st.cur] = st.acc;
+        __syncthreads();            /* panel p consumed: its x buffer and the sums are free */
+    }
+    for (int i = tid; i < R; i += Tn) {
+        const int row = rb * R + i;
+        if (row < rows) y[row] = sums[i];
+    }
+}
+
+static size_t ring_bytes(const DevPanel &pm, bool f32)
+{
+    return (size_t)(pm.R / pm.G / 32) * pm.ring_S * pm.ring_K * 32 * ((f32 ? 8 : 16) + 4);
+}
+
+size_t panelr_smem_bytes(const DevPanel &pm, bool f32)
+{
+    const size_t es = f32 ? 4 : 8;
+    const size_t soff = 16 + (size_t)(pm.R / pm.G / 32) * pm.ring_S * 8;
+    const size_t xoff = (soff + (size_t)(pm.R + 1) * es + 15) & ~(size_t)15;
+    const size_t ws = (size_t)pm.W + 16 / es;
+    const size_t roff = (xoff + (size_t)pm.nbuf * ws * es + 127) & ~(size_t)127;
+    return roff + ring_bytes(pm, f32);
+}
+
+template <typename T, int G, int K, int MAXT>
+static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(spmv_panelr_kernel<T, G, K, MAXT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    const size_t smem = panelr_smem_bytes(pm, sizeof(T) == 4);
+    const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
+    spmv_panelr_kernel<T, G, K, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
+        static_cast<const T *>(pm.val), pm.col, pm.rowids, pm.slice_off, x, y,
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S);
+}
+
+template <typename T, int G>
+static void launch_panelr_g(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+{
+    const int threads = pm.R / pm.G;
+    if (threads > 512) {
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 768>(pm, x, y, s);
+        else                launch_panelr_cfg<T, G, 4, 768>(pm, x, y, s);
+    } else {
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 512>(pm, x, y, s);
+        else                launch_panelr_cfg<T, G, 4, 512>(pm, x, y, s);
+    }
+}
+
+template <typename T>
+void launch_panelr(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+{
+    if (pm.nblk <= 0) return;
+    if (pm.G == 2)      launch_panelr_g<T, 2>(pm, x, y, s);
+    else if (pm.G == 4) launch_panelr_g<T, 4>(pm, x, y, s);
+    else                launch_panelr_g<T, 8>(pm, x, y, s);
+}
+template void launch_panelr<double>(const DevPanel &, const double *, double *, cudaStream_t);
+template void launch_panelr<float>(const DevPanel &, const float *, float *, cudaStream_t);
+
+}  // namespace b200

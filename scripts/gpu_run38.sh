@@ -1,0 +1,6 @@
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "flagged" 2>&1 | tail -3
+export B200_SPMV_VERBOSE=1
+timeout 400 python scripts/sweep.py D/8 "sell,pr:S=2,pr:S=2;B=1,pr:S=3,pr:S=3;B=1" 30 2>&1 | grep -v "kernel=\(vector\|ordered\|sell\) panel" | tee gpurun_out/sweep38.txt
+timeout 300 python scripts/sweep.py C "panel,pr:G=2;S=2,pr:G=2;S=3" 100 2>&1 | grep -v "kernel=\(vector\|ordered\|sell\) panel" | tee -a gpurun_out/sweep38.txt
+timeout 300 python scripts/sweep.py D/4 "pr:S=2,pr:S=2;B=1" 30 2>&1 | grep -v "kernel=\(vector\|ordered\|sell\) panel" | tee -a gpurun_out/sweep38.txt
+timeout 600 python scripts/sweep.py D "pr:S=2,pr:S=2;B=1" 10 2>&1 | grep -v "kernel=\(vector\|ordered\|sell\) panel" | tee -a gpurun_out/sweep38.txt

@@ -47,17 +47,31 @@ xs = [torch.from_numpy(rng.random(ncols + 2)).cuda() for _ in range(4)]
 y = torch.zeros(m.n, dtype=torch.float64, device="cuda")
 B = 12 * m.nnz + 4 * (m.n + 1) + 8 * ncols + 8 * m.n
 y_ref = None
-for cfg in configs:
+for cfg_full in configs:
+    # "cfg!NAME=V!NAME2=V2" adds B200_SPMV_PANEL_<NAME>=V to the environment of that upload
+    cfg, *extras = cfg_full.split("!")
     env = {}
+    for kv in extras:
+        k, v = kv.split("=")
+        env["B200_SPMV_PANEL_" + k] = v
     kernel = cfg
     if cfg.startswith("sell:"):
         kernel = "sell"
         for kv in cfg[5:].split(";"):
             k, v = kv.split("=")
             env["B200_SPMV_SELL_" + {"R": "ROWS", "G": "G", "U": "U", "C": "CAP"}[k]] = v
+    elif cfg.startswith("pg") or cfg.startswith("pr"):
+        # flagged-stream panel, register-staged ("pg") or ring ("pr"): "pr:R=1280;G=4;W=12288;B=2;K=4;Q=96"
+        kernel = "panel"
+        env["B200_SPMV_PANEL_FMT"] = "1" if cfg.startswith("pg") else "2"
+        for kv in cfg[3:].split(";"):
+            if not kv:
+                continue
+            k, v = kv.split("=")
+            env["B200_SPMV_PANEL_" + {"R": "ROWS", "G": "G", "W": "COLS", "B": "NBUF", "T": "TMA", "K": "RING_K", "Q": "RING_KB", "S": "RING_S", "M": "SMEM_KB"}[k]] = v
     elif "x" in cfg and cfg[0].isdigit():
         parts = cfg.split("x")
-        env = {"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]}
+        env.update({"B200_SPMV_PANEL_COLS": parts[0], "B200_SPMV_PANEL_ROWS": parts[1]})
         for opt in parts[2:]:
             if opt == "notma":
                 env["B200_SPMV_PANEL_TMA"] = "0"
@@ -86,7 +100,7 @@ for cfg in configs:
     if y_ref is None:
         y_ref = yy.copy()
     same = bool(np.array_equal(yy, y_ref))
-    print(f"{cls} {cfg:>22s} kernel={rm.kernel_name:8s} {us:9.1f} us  {B / us / 1e3:8.1f} GB/s  "
+    print(f"{cls} {cfg_full:>26s} kernel={rm.kernel_name:8s} {us:9.1f} us  {B / us / 1e3:8.1f} GB/s  "
           f"frac={B / us / 1e3 / 6533.5:5.3f}  same_as_first={same}", flush=True)
     rm.release()
     for k in env:

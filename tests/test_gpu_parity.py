@@ -136,6 +136,41 @@ def test_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, pa
     assert m2.kernel_name == "ordered" and np.array_equal(y2, y0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [
+    dict(n=1, ncols=1, mean=1), dict(n=33, ncols=70, mean=9), dict(n=1000, ncols=1000, mean=25),
+    dict(n=5000, ncols=40000, mean=130), dict(n=300, ncols=70000, mean=900),
+    dict(n=9000, ncols=131072, mean=64), dict(n=4500, ncols=1500000, mean=450),
+])
+@pytest.mark.parametrize("panel_env", [
+    {"B200_SPMV_PANEL_G": 2}, {"B200_SPMV_PANEL_G": 4}, {"B200_SPMV_PANEL_G": 8},
+    {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_COLS": 256, "B200_SPMV_PANEL_ROWS": 256},
+    {"B200_SPMV_PANEL_G": 8, "B200_SPMV_PANEL_COLS": 4096, "B200_SPMV_PANEL_ROWS": 4096},
+    {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_NBUF": 1},
+    {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 700, "B200_SPMV_PANEL_TMA": 0},
+])
+@pytest.mark.parametrize("fmt", [2, 1])
+def test_flagged_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, panel_env, fmt):
+    """Tall row blocks with G rows per lane stream (the layout for wide
+    matrices such as NPB class D row blocks; fmt 2 = spmv_panelr.cu, the
+    matrix stream through a shared-memory ring, fmt 1 = spmv_panelg.cu,
+    register-staged): bit-identical to the reference loop for every G,
+    row-block height and panel width, including duplicate columns, empty rows
+    and ragged last blocks."""
+    rng = np.random.default_rng(shape["n"] * 11 + shape["mean"])
+    lens = rng.poisson(shape["mean"], shape["n"])
+    lens[rng.random(shape["n"]) < 0.1] = 0
+    a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=True)
+    y0 = oracle.spmv(a, x, rowstr, c)
+    env = dict(panel_env, B200_SPMV_PANEL_FMT=fmt)
+    if shape["ncols"] > 500 * env.get("B200_SPMV_PANEL_COLS", shape["ncols"]):
+        del env["B200_SPMV_PANEL_COLS"]          # more than 512 panels: the plan is refused
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "panel", env)
+    if len(c):
+        assert m.kernel_name == "panel", (m.kernel_name, m.ncols, m.nnz)
+    assert np.array_equal(y, y0)
+
+
 def test_panel_falls_back_when_rows_are_unsorted(libspmv, oracle):
     rng = np.random.default_rng(77)
     a, c, rowstr, x = make_csr(rng, 2000, 3000, rng.poisson(40, 2000), sort=False)
