@@ -75,6 +75,15 @@ __device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT
     }
 }
 
+/* pairs walked for a slice of npair pairs: whole double chunks, and one double chunk
+ * even for an empty slice -- the consumer loop runs once for it too, so cursor and
+ * consumer always spend the same number of chunks per panel */
+template <int U>
+__device__ __forceinline__ int cursor_rounds(int npair)
+{
+    return (max(npair, 1) + 2 * U - 1) / (2 * U) * (2 * U);
+}
+
 /* Read cursor over a lane stream: walks the pairs of panel 0, 1, ... of this
  * warp's slices in chunks of U pairs, so that the matrix stream stays
  * requested ahead of its use across panel boundaries.  Every panel is walked
@@ -87,25 +96,6 @@ struct StreamCursor {
     size_t base;    /* pair offset of the slice + lane */
 };
 
-/* position the cursor on the first non-empty slice at or after panel cur.p
- * (the consumer spends no chunk on an empty slice, so neither may the cursor) */
-template <int U>
-__device__ __forceinline__ void cursor_seek(StreamCursor &cur, const int2 *s_slice, int spb,
-                                            int warp, int lane, int P)
-{
-    while (cur.p < P) {
-        const int2 so = s_slice[cur.p * spb + warp];
-        if (so.y > 0) {
-            cur.kp = 0;
-            cur.npair = so.y;
-            cur.nround = (so.y + 2 * U - 1) / (2 * U) * (2 * U);
-            cur.base = (size_t)(so.x >> 1) + lane;
-            return;
-        }
-        ++cur.p;
-    }
-}
-
 template <typename T, int U>
 __device__ __forceinline__ void cursor_load(Chunk<T, U> &ch, StreamCursor &cur,
                                             const typename PairT<T>::type *val2,
@@ -117,7 +107,13 @@ __device__ __forceinline__ void cursor_load(Chunk<T, U> &ch, StreamCursor &cur,
         cur.kp += U;
         if (cur.kp >= cur.nround) {
             ++cur.p;
-            cursor_seek<U>(cur, s_slice, spb, warp, lane, P);
+            if (cur.p < P) {
+                const int2 so = s_slice[cur.p * spb + warp];
+                cur.kp = 0;
+                cur.npair = so.y;
+                cur.nround = cursor_rounds<U>(so.y);
+                cur.base = (size_t)(so.x >> 1) + lane;
+            }
         }
     }
 }

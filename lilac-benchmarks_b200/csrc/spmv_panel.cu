@@ -323,8 +323,12 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
     /* request the first two chunks of the matrix stream */
     StreamCursor cur;
-    cur.p = 0; cur.kp = 0; cur.npair = 0; cur.nround = 0; cur.base = 0;
-    cursor_seek<U>(cur, s_slice, spb, warp, lane, P);
+    {
+        const int2 so = s_slice[warp];
+        cur.p = 0; cur.kp = 0; cur.npair = so.y;
+        cur.nround = cursor_rounds<U>(so.y);
+        cur.base = (size_t)(so.x >> 1) + lane;
+    }
     Chunk<T, U> a, b;
     cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
     cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);
@@ -354,7 +358,8 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         int row_cur = mt.x;
         const int row_nxt = mt.y, sw = mt.z;
         T acc = sums[row_cur];
-        for (int kp = 0; kp < npair; kp += 2 * U) {
+        /* an empty slice still takes one (fully predicated) round: see cursor_rounds() */
+        for (int kp = 0; kp < max(npair, 1); kp += 2 * U) {
             acc = consume_chunk<T, U>(a, xs, sums, acc, kp, npair, sw, row_cur, row_nxt);
             cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
             acc = consume_chunk<T, U>(b, xs, sums, acc, kp + U, npair, sw, row_cur, row_nxt);

@@ -196,24 +196,15 @@ __device__ __forceinline__ T consume_flagged(const Chunk<T, U> &ch, const T *xs,
     return acc;
 }
 
-/* the read cursor (panel_common.cuh) over a one-int-per-slice offset table;
- * empty slices are skipped (the consumer spends no chunk on them either) */
+/* the read cursor (panel_common.cuh) over a one-int-per-slice offset table */
 template <int U>
-__device__ __forceinline__ void cursor_seek(StreamCursor &cur, const int *s_off, int spb,
-                                            int warp, int lane, int P)
+__device__ __forceinline__ void cursor_open(StreamCursor &cur, const int *s_off, int slice, int lane)
 {
-    while (cur.p < P) {
-        const int o = s_off[cur.p * spb + warp];
-        const int np = (s_off[cur.p * spb + warp + 1] - o) >> 6;
-        if (np > 0) {
-            cur.kp = 0;
-            cur.npair = np;
-            cur.nround = (np + 2 * U - 1) / (2 * U) * (2 * U);
-            cur.base = (size_t)(o >> 1) + lane;
-            return;
-        }
-        ++cur.p;
-    }
+    const int o = s_off[slice];
+    cur.kp = 0;
+    cur.npair = (s_off[slice + 1] - o) >> 6;
+    cur.nround = cursor_rounds<U>(cur.npair);
+    cur.base = (size_t)(o >> 1) + lane;
 }
 
 template <typename T, int U>
@@ -227,7 +218,7 @@ __device__ __forceinline__ void cursor_next(Chunk<T, U> &ch, StreamCursor &cur,
         cur.kp += U;
         if (cur.kp >= cur.nround) {
             ++cur.p;
-            cursor_seek<U>(cur, s_off, spb, warp, lane, P);
+            if (cur.p < P) cursor_open<U>(cur, s_off, cur.p * spb + warp, lane);
         }
     }
 }
@@ -311,8 +302,8 @@ spmv_panelg_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     }
 
     StreamCursor cur;
-    cur.p = 0; cur.kp = 0; cur.npair = 0; cur.nround = 0; cur.base = 0;
-    cursor_seek<U>(cur, s_off, spb, warp, lane, P);
+    cur.p = 0;
+    cursor_open<U>(cur, s_off, warp, lane);
     Chunk<T, U> a, b;
     cursor_next<T, U>(a, cur, val2, col2, s_off, spb, warp, lane, P);
     cursor_next<T, U>(b, cur, val2, col2, s_off, spb, warp, lane, P);
@@ -337,7 +328,8 @@ spmv_panelg_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
         int row_cur = R;                                  /* dummy slot until the first flag */
         T acc = (T)0;
-        for (int kp = 0; kp < npair; kp += 2 * U) {
+        /* an empty slice still takes one (fully predicated) round: see cursor_rounds() */
+        for (int kp = 0; kp < max(npair, 1); kp += 2 * U) {
             acc = consume_flagged<T, U, G>(a, xs, sums, acc, kp, npair, row_cur, ids);
             cursor_next<T, U>(a, cur, val2, col2, s_off, spb, warp, lane, P);
             acc = consume_flagged<T, U, G>(b, xs, sums, acc, kp + U, npair, row_cur, ids);
