@@ -55,12 +55,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic(workload, kernel):
+def recorded_traffic(workload, kernel, world=1):
     """DRAM bytes per launch from the committed ncu --set full capture, if any."""
     p = ROOT / "profiles" / "roofline_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(f"{workload}:{kernel}")
+            key = f"{workload}:{kernel}" + (f"@{world}" if world > 1 else "")
+            return json.loads(p.read_text()).get(key)
         except Exception:
             return None
     return None
@@ -394,11 +395,12 @@ def run_b200(args, world, rank, local_rank):
                         else "allgather of x per step (NCCL)"),
                        "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                        "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
-                           "ms_per_step": 2.7398, "value": 3052.3, "unit": UNIT,
-                           "source": "profiles/r01_run20_classD_full_one_gpu.txt (class D, SELL kernel, 1xB200)"},
+                           "ms_per_step": 1.9094, "value": 4379.7, "unit": UNIT,
+                           "source": "profiles/r01_run35_sweep_ring_classD_full.txt (class D, ring PANEL kernel, "
+                                     "1xB200; SELL kernel: 2.738 ms)"},
                        "gen_s": round(t_gen, 2), "upload_s": round(t_upload, 3)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": recorded_traffic(label, rm.kernel_name),
+                         "frac": ach / peak, "traffic": recorded_traffic(label, rm.kernel_name, world),
                          "peak_source": peak_src,
                          "kernel": f"spmv ({rm.kernel_name})" + ("" if world == 1 else " + exchange, per rank")},
             "e2e": {"value": B / e2e_sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
