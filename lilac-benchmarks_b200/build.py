@@ -14,7 +14,7 @@ CSRC = PKG / "csrc"
 CALLERS = PKG / "callers"
 ORACLE = ROOT / "oracle"
 
-B200_SO = CSRC / "b200.so"
+B200_SO = Path(os.environ.get("B200_SPMV_SO", CSRC / "b200.so"))   # override: experiment builds
 CALLERS_SO = CALLERS / "libb200callers.so"
 ORACLE_SO = ORACLE / "liboracle.so"
 REF_NATIVE_SO = ORACLE / "_ref" / "native.so"

@@ -438,7 +438,8 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
         const double seg_d = (double)m->nnz / ((double)m->rows * Pd);
         if (force_nbuf == 1 || (force_nbuf == 0 && !getenv("B200_SPMV_PANEL_COLS") && seg_d < 8.0)) {
             nbuf = 1;
-            wmax = width_that_fits(1, std::min(kMaxPanels, (m->ncols + 16383) / 16384 + 1));
+            const int w1 = width_that_fits(1, std::min(kMaxPanels, (m->ncols + 16383) / 16384 + 1));
+            wmax = getenv("B200_SPMV_PANEL_COLS") ? std::min(wmax, w1) : w1;
         }
         wmax = std::max(32, std::min(wmax, width_that_fits(nbuf, std::min(kMaxPanels, Pd + 1)))) & ~31;
         P = (m->ncols + wmax - 1) / wmax;

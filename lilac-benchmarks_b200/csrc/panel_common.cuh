@@ -56,6 +56,38 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+/* loads of the matrix stream: read once.  B200_STREAM_LD selects the cache operator:
+ * 1 = ld.global.nc.L1::no_allocate (SASS LDG.E.NA; class C 74.4 us), 0 = ld.global.cs
+ * (evict first; 75.7 us), 2 = plain non-coherent (77.9 us) -- profiles/r01_run42_sweep_ld_operator.txt */
+#ifndef B200_STREAM_LD
+#define B200_STREAM_LD 1
+#endif
+__device__ __forceinline__ double2 ld_matrix_stream(const double2 *p)
+{
+#if B200_STREAM_LD == 1
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#elif B200_STREAM_LD == 2
+    return __ldg(p);
+#else
+    return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ float2 ld_matrix_stream(const float2 *p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_matrix_stream(const uint32_t *p)
+{
+#if B200_STREAM_LD == 1
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+#elif B200_STREAM_LD == 2
+    return __ldg(p);
+#else
+    return __ldcs(p);
+#endif
+}
+
 template <typename T, int U>
 struct Chunk {
     typename PairT<T>::type v[U];
@@ -69,8 +101,8 @@ __device__ __forceinline__ void load_chunk(Chunk<T, U> &ch, const typename PairT
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (kp + u < npair) {
-            ch.v[u] = __ldcs(vp + (size_t)(kp + u) * 32);
-            ch.c[u] = __ldcs(cp + (size_t)(kp + u) * 32);
+            ch.v[u] = ld_matrix_stream(vp + (size_t)(kp + u) * 32);
+            ch.c[u] = ld_matrix_stream(cp + (size_t)(kp + u) * 32);
         }
     }
 }
