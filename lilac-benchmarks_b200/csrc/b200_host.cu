@@ -319,16 +319,18 @@ static const size_t kSmemMax = 227 * 1024;
 
 struct PanelPlan { int P, W, R, G, nbuf, fmt, ring_K, ring_S; };
 
-/* fmt 1 (spmv_panelg.cu): tall row blocks of G * T rows for wide matrices.
- * One CTA per SM and as few passes over x as the shared-memory budget
- * (R + 1 running sums) allows; the rest of the 227 KB holds two x slices. */
-static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl, int fmt)
+/* RING layout (spmv_panelg.cu + spmv_panelr.cu): tall row blocks of G * T rows for
+ * wide matrices.  One CTA per SM and as few passes over x as the shared-memory
+ * budget (R + 1 running sums) allows; the rest of the 227 KB holds the per-warp
+ * rings of the matrix stream and two x slices. */
+static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl)
 {
+    const int fmt = 2;
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
     const size_t es = elem_size(m->dtype);
     const int kRmax = 4096, kMaxPanels = 512;
-    const int kTmax = fmt == 2 ? std::max(64, std::min(768, env_int("B200_SPMV_PANEL_TMAX", 512))) : 512;
+    const int kTmax = std::max(64, std::min(768, env_int("B200_SPMV_PANEL_TMAX", 512)));
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) {
         const int passes = (int)((m->rows + (long long)g_sm_count * kRmax - 1) / ((long long)g_sm_count * kRmax));
@@ -342,15 +344,12 @@ static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl, int fmt)
     R = Tn * G;
     const int spb = Tn / 32;
     int nbuf = env_int("B200_SPMV_PANEL_NBUF", 2) == 1 ? 1 : 2;
-    /* fmt 1: shared memory and L1 share 256 KB per SM, and the matrix stream needs L1 lines
-     * for its loads in flight: leaving the L1 less than ~50 KB costs more than wider panels
-     * gain (class C: 76 us at 202 KB of shared memory, 91 us at 227 KB; profiles/r01_run5_sweep.txt).
-     * fmt 2: the stream lands in a shared-memory ring (S stages of K pair rows per warp),
-     * nothing is left for the L1 to do, so the whole 227 KB is used. */
+    /* the stream lands in a shared-memory ring (S stages of K pair rows per warp), nothing
+     * is left for the L1 to do, so the whole 227 KB is used */
     int ring_K = 0, ring_S = 0;
     size_t ring = 0;
-    size_t budget = std::min<size_t>(kSmemMax, (size_t)env_int("B200_SPMV_PANEL_SMEM_KB", fmt == 2 ? 227 : 200) * 1024);
-    if (fmt == 2) {
+    const size_t budget = std::min<size_t>(kSmemMax, (size_t)env_int("B200_SPMV_PANEL_SMEM_KB", 227) * 1024);
+    {
         ring_K = env_int("B200_SPMV_PANEL_RING_K", 4) == 2 ? 2 : 4;
         const size_t stage = (size_t)spb * ring_K * 32 * (2 * es + 4);
         /* two stages per warp: a deeper ring takes the room from the x slices, and more,
@@ -359,8 +358,8 @@ static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl, int fmt)
         ring = stage * ring_S + (size_t)spb * ring_S * 8 + 256;
     }
     auto width_that_fits = [&](int P) {
-        const size_t table = fmt == 2 ? 0 : ((size_t)P * spb + 1) * 4;
-        const size_t fixed = ((((16 + table + 7) & ~(size_t)7) + (size_t)(R + 1) * es + 15) & ~(size_t)15) + 64 + ring;
+        (void)P;
+        const size_t fixed = (((size_t)16 + (size_t)(R + 1) * es + 15) & ~(size_t)15) + 64 + ring;
         if (fixed >= budget) return 0;
         return (int)(std::min<long long>(32736, (long long)((budget - fixed) / (nbuf * es)) - 4) & ~31);
     };
@@ -466,7 +465,7 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     if (!ok && want_fmt != 0) {
         /* wide matrices: tall row blocks, G rows per lane (spmv_panelg.cu) */
         PanelPlan pl;
-        if (panel_plan_flagged(m, &pl, want_fmt == 1 ? 1 : 2) && (forced || panel_plan_beats_sell(m, pl))) {
+        if (panel_plan_flagged(m, &pl) && (forced || panel_plan_beats_sell(m, pl))) {
             P = pl.P; W = pl.W; R = pl.R; G = pl.G; nbuf = pl.nbuf; fmt = pl.fmt;
             ring_K = pl.ring_K; ring_S = pl.ring_S;
             ok = true;
@@ -487,11 +486,11 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
     launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
-    /* fmt 0: one ushort4 per lane and tile; fmt 1: G row ids per lane and tile */
-    const size_t meta_bytes = fmt >= 1 ? (size_t)ntiles * R * sizeof(uint16_t) : (size_t)ntiles * Tn * sizeof(ushort4);
+    /* fmt 0: one ushort4 per lane and tile; fmt 2: G row ids per lane and tile */
+    const size_t meta_bytes = fmt == 2 ? (size_t)ntiles * R * sizeof(uint16_t) : (size_t)ntiles * Tn * sizeof(ushort4);
     CUDA_OK(cudaMalloc((void **)&m->d_meta, meta_bytes));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    if (fmt >= 1)
+    if (fmt == 2)
         launch_panelg_sort(d_seglen, ntiles, R, G, reinterpret_cast<uint16_t *>(m->d_meta), d_cnt, g_stream);
     else
         launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, g_stream);
@@ -542,7 +541,7 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     pm.use_tma = env_int("B200_SPMV_PANEL_TMA", 1);
     pm.nbuf = nbuf;
     pm.padded = run;
-    if (fmt >= 1) {
+    if (fmt == 2) {
         if (m->dtype == B200_F64)
             launch_panelg_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
                                        d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
@@ -558,8 +557,7 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(g_stream));
     CUDA_OK(cudaFree(d_seglen));
-    if ((fmt == 2 ? panelr_smem_bytes(pm, m->dtype == B200_F32) :
-         fmt == 1 ? panelg_smem_bytes(pm, m->dtype == B200_F32) : panel_smem_bytes(pm, m->dtype == B200_F32)) > kSmemMax)
+    if ((fmt == 2 ? panelr_smem_bytes(pm, m->dtype == B200_F32) : panel_smem_bytes(pm, m->dtype == B200_F32)) > kSmemMax)
         die("panel shared-memory budget exceeded (W=%d R=%d)", W, R);
     /* the CSR copy of val / col is no longer needed */
     CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;
@@ -824,11 +822,6 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
                 launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, s);
             else
                 launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, s);
-        } else if (m->panel.fmt == 1) {
-            if (m->dtype == B200_F64)
-                launch_panelg<double>(m->panel, (const double *)d_x, (double *)d_y, s);
-            else
-                launch_panelg<float>(m->panel, (const float *)d_x, (float *)d_y, s);
         } else if (m->dtype == B200_F64)
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else

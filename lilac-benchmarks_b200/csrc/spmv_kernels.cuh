@@ -64,13 +64,13 @@ struct DevPanel {
     const void     *val;        /* T[padded], tile-major SELL-pair order */
     const uint16_t *col;        /* u16[padded], 0-based column inside its panel; W = +0.0 slot */
     const ushort4  *meta;       /* fmt 0: [nblk * P * R/G]: {row A, row B, pair where B starts, 0} */
-    const uint16_t *rowids;     /* fmt 1: [nblk * P * R]: the G tile-local row ids of every lane */
+    const uint16_t *rowids;     /* fmt 2: [nblk * P * R]: the G tile-local row ids of every lane */
     const int      *slice_off;  /* int[nblk * P * R/32 + 1], element offsets (multiples of 64) */
     int rows, ncols;
     int R;                      /* rows per row block (multiple of 32 G) */
-    int G;                      /* rows per thread (fmt 0: 1 or 2; fmt 1: 2, 4 or 8); the CTA has R/G threads */
-    int fmt;                    /* 0: paired rows (spmv_panel.cu); 1: flagged streams (spmv_panelg.cu);
-                                 * 2: flagged streams, warp-major, through a shared-memory ring (spmv_panelr.cu) */
+    int G;                      /* rows per thread (fmt 0: 1 or 2; fmt 2: 2, 4 or 8); the CTA has R/G threads */
+    int fmt;                    /* 0: paired rows (spmv_panel.cu); 2: flagged streams, warp-major,
+                                 * through a shared-memory ring (spmv_panelg.cu, spmv_panelr.cu) */
     int ring_K, ring_S;         /* fmt 2: pair rows per ring stage, stages per warp */
     int U;                      /* pairs per prefetch chunk (tuning) */
     int P;                      /* number of column panels */
@@ -95,17 +95,14 @@ template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
 size_t panel_smem_bytes(const DevPanel &pm, bool f32);
 
-/* flagged-stream variant for wide matrices (fmt 1, spmv_panelg.cu) */
+/* flagged-stream layout for wide matrices: build passes (spmv_panelg.cu) */
 void launch_panelg_sort(const uint16_t *seglen, int ntiles, int R, int G, uint16_t *rowids,
                         int *slice_elems, cudaStream_t s);
 template <typename T>
 void launch_panelg_fill(const T *val, const int *col, const int *rowptr, int rows,
                         const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
                         cudaStream_t s);
-template <typename T>
-void launch_panelg(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
-size_t panelg_smem_bytes(const DevPanel &pm, bool f32);
-/* ring variant (fmt 2, spmv_panelr.cu); same build passes, slices in (row block, warp, panel) order */
+/* ... and its kernel: the matrix stream through per-warp shared-memory rings (spmv_panelr.cu) */
 template <typename T>
 void launch_panelr(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
 size_t panelr_smem_bytes(const DevPanel &pm, bool f32);

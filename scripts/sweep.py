@@ -60,10 +60,10 @@ for cfg_full in configs:
         for kv in cfg[5:].split(";"):
             k, v = kv.split("=")
             env["B200_SPMV_SELL_" + {"R": "ROWS", "G": "G", "U": "U", "C": "CAP"}[k]] = v
-    elif cfg.startswith("pg") or cfg.startswith("pr"):
-        # flagged-stream panel, register-staged ("pg") or ring ("pr"): "pr:R=1280;G=4;W=12288;B=2;K=4;Q=96"
+    elif cfg.startswith("pr"):
+        # ring panel for wide matrices: "pr:R=1280;G=4;W=12288;B=2;K=4;S=2"
         kernel = "panel"
-        env["B200_SPMV_PANEL_FMT"] = "1" if cfg.startswith("pg") else "2"
+        env["B200_SPMV_PANEL_FMT"] = "2"
         for kv in cfg[3:].split(";"):
             if not kv:
                 continue

@@ -148,21 +148,22 @@ def test_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, pa
     {"B200_SPMV_PANEL_G": 8, "B200_SPMV_PANEL_COLS": 4096, "B200_SPMV_PANEL_ROWS": 4096},
     {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_NBUF": 1},
     {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 700, "B200_SPMV_PANEL_TMA": 0},
+    {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_RING_K": 2, "B200_SPMV_PANEL_RING_S": 3},
+    {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_TMAX": 640, "B200_SPMV_PANEL_RING_S": 5},
 ])
-@pytest.mark.parametrize("fmt", [2, 1])
-def test_flagged_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, panel_env, fmt):
-    """Tall row blocks with G rows per lane stream (the layout for wide
-    matrices such as NPB class D row blocks; fmt 2 = spmv_panelr.cu, the
-    matrix stream through a shared-memory ring, fmt 1 = spmv_panelg.cu,
-    register-staged): bit-identical to the reference loop for every G,
-    row-block height and panel width, including duplicate columns, empty rows
-    and ragged last blocks."""
+def test_ring_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, panel_env):
+    """Tall row blocks with G rows per lane stream and the matrix stream
+    through per-warp shared-memory rings (spmv_panelg.cu + spmv_panelr.cu, the
+    layout for wide matrices such as NPB class D row blocks): bit-identical to
+    the reference loop for every G, row-block height, panel width and ring
+    geometry, including duplicate columns, empty rows and ragged last
+    blocks."""
     rng = np.random.default_rng(shape["n"] * 11 + shape["mean"])
     lens = rng.poisson(shape["mean"], shape["n"])
     lens[rng.random(shape["n"]) < 0.1] = 0
     a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=True)
     y0 = oracle.spmv(a, x, rowstr, c)
-    env = dict(panel_env, B200_SPMV_PANEL_FMT=fmt)
+    env = dict(panel_env, B200_SPMV_PANEL_FMT=2)
     if shape["ncols"] > 500 * env.get("B200_SPMV_PANEL_COLS", shape["ncols"]):
         del env["B200_SPMV_PANEL_COLS"]          # more than 512 panels: the plan is refused
     m, y = _exec_resident(libspmv, a, x, rowstr, c, "panel", env)
