@@ -149,7 +149,7 @@ def test_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, pa
     {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_NBUF": 1},
     {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 700, "B200_SPMV_PANEL_TMA": 0},
     {"B200_SPMV_PANEL_G": 4, "B200_SPMV_PANEL_RING_K": 2, "B200_SPMV_PANEL_RING_S": 3},
-    {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_TMAX": 640, "B200_SPMV_PANEL_RING_S": 5},
+    {"B200_SPMV_PANEL_G": 2, "B200_SPMV_PANEL_ROWS": 1280, "B200_SPMV_PANEL_TMAX": 640, "B200_SPMV_PANEL_RING_K": 2, "B200_SPMV_PANEL_RING_S": 3},
 ])
 def test_ring_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shape, panel_env):
     """Tall row blocks with G rows per lane stream and the matrix stream
