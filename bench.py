@@ -327,25 +327,26 @@ def run_b200(args, world, rank, local_rank):
         hx = [torch.from_numpy(rng.random(ncols + 2)).pin_memory() for _ in range(4)]
         hy = torch.zeros(m.n, dtype=torch.float64).pin_memory()
         hx_np, hy_np = [t.numpy() for t in hx], hy.numpy()
-        for i in range(3):
-            libspmv.spmv_harness(hy_np, m.a, hx_np[i & 3], m.rowstr, m.colidx, m.n)
+        # the calls are issued by the C caller loop of callers/npb (what a compiled caller of
+        # the ABI such as cg.f pays per call; a ctypes call from Python adds ~15-30 us of
+        # argument marshalling that is not the library's)
+        addr = libspmv.harness_address()
+        npb.time_spmv_calls(addr, hy_np, m.a, hx_np, m.rowstr, m.colidx, m.n, 3)
         libspmv.reset_stats()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            libspmv.spmv_harness(hy_np, m.a, hx_np[i & 3], m.rowstr, m.colidx, m.n)
-        e2e_sec = (time.perf_counter() - t0) / Ke
+        e2e_sec = npb.time_spmv_calls(addr, hy_np, m.a, hx_np, m.rowstr, m.colidx, m.n, Ke)
         st = libspmv.stats()
         h2d, d2h = st["h2d_bytes"] // Ke, st["d2h_bytes"] // Ke
         e2e_kernel_ms = st["kernel_ms"] / Ke
         # pageable caller vectors (what NPB's COMMON arrays are): pinned bounce inside the library
         px = [np.array(v) for v in hx_np]
         py = np.zeros(m.n)
-        for i in range(3):
-            libspmv.spmv_harness(py, m.a, px[i & 3], m.rowstr, m.colidx, m.n)
+        npb.time_spmv_calls(addr, py, m.a, px, m.rowstr, m.colidx, m.n, 3)
+        e2e_pageable_sec = npb.time_spmv_calls(addr, py, m.a, px, m.rowstr, m.colidx, m.n, min(Ke, 500))
+        # the same pinned-vector call issued from Python through ctypes
         t0 = time.perf_counter()
         for i in range(min(Ke, 500)):
-            libspmv.spmv_harness(py, m.a, px[i & 3], m.rowstr, m.colidx, m.n)
-        e2e_pageable_sec = (time.perf_counter() - t0) / min(Ke, 500)
+            libspmv.spmv_harness(hy_np, m.a, hx_np[i & 3], m.rowstr, m.colidx, m.n)
+        e2e_python_sec = (time.perf_counter() - t0) / min(Ke, 500)
     else:
         lo, hi = layout.local_range(rank)
         hx = torch.from_numpy(rng.random(hi - lo)).pin_memory()
@@ -371,6 +372,7 @@ def run_b200(args, world, rank, local_rank):
         h2d = d2h = n_global * 8          # summed over ranks
         e2e_kernel_ms = None
         e2e_pageable_sec = None
+        e2e_python_sec = None
 
     line = None
     if rank == 0:
@@ -395,9 +397,9 @@ def run_b200(args, world, rank, local_rank):
                         else "allgather of x per step (NCCL)"),
                        "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                        "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
-                           "ms_per_step": 1.9094, "value": 4379.7, "unit": UNIT,
-                           "source": "profiles/r01_run35_sweep_ring_classD_full.txt (class D, ring PANEL kernel, "
-                                     "1xB200; SELL kernel: 2.738 ms)"},
+                           "ms_per_step": 1.6313, "value": 5126.4, "unit": UNIT,
+                           "source": "profiles/r01_run48_sweep_ring_single_buffer.txt (class D, ring PANEL "
+                                     "kernel, 1xB200; SELL kernel: 2.738 ms)"},
                        "gen_s": round(t_gen, 2), "upload_s": round(t_upload, 3)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": recorded_traffic(label, rm.kernel_name, world),
@@ -405,10 +407,12 @@ def run_b200(args, world, rank, local_rank):
                          "kernel": f"spmv ({rm.kernel_name})" + ("" if world == 1 else " + exchange, per rank")},
             "e2e": {"value": B / e2e_sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3, "steps": Ke,
-                    "api": "spmv_harness_ (pinned caller vectors)" if world == 1
+                    "api": "spmv_harness_ called from the C caller loop (callers/npb), pinned caller vectors"
+                    if world == 1
                     else "ShardedSpmv.step with pinned host slices",
                     "kernel_ms_per_step": e2e_kernel_ms,
-                    "pageable_ms_per_step": None if e2e_pageable_sec is None else e2e_pageable_sec * 1e3},
+                    "pageable_ms_per_step": None if e2e_pageable_sec is None else e2e_pageable_sec * 1e3,
+                    "python_ctypes_ms_per_step": None if e2e_python_sec is None else e2e_python_sec * 1e3},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
         }

@@ -189,3 +189,12 @@ int npb_cg_run(const npb_cg_class *c, const npb_csr *m, spmv_harness_fn harness,
     free(x); free(z); free(p); free(q); free(r);
     return 0;
 }
+
+double npb_time_spmv_calls(spmv_harness_fn harness, double *ov, double *a, double *const *xs, int nx,
+                           int *rowstr, int *colidx, int rows, int calls)
+{
+    int n = rows;                       /* passed by reference, as Fortran does */
+    const double t0 = wtime();
+    for (int i = 0; i < calls; ++i) harness(ov, a, xs[i % nx], rowstr, colidx, &n);
+    return wtime() - t0;
+}

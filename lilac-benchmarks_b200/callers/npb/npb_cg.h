@@ -79,6 +79,14 @@ void npb_conj_grad(const npb_csr *m, spmv_harness_fn harness,
                    double *x, double *z, double *p, double *q, double *r,
                    double *rnorm);
 
+/* `calls` back-to-back products through `harness`, issued the way conj_grad's
+ * hot loop issues them (cg.f:531-532): one matrix, x rotating over the nx
+ * caller vectors xs[0..nx), y always into ov.  Returns the wall-clock
+ * seconds of the loop (what a compiled caller pays per ABI call, without
+ * any scripting-language marshalling). */
+double npb_time_spmv_calls(spmv_harness_fn harness, double *ov, double *a, double *const *xs, int nx,
+                           int *rowstr, int *colidx, int rows, int calls);
+
 double npb_randlc(double *x, double a);
 
 #ifdef __cplusplus

@@ -343,7 +343,9 @@ static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl)
     Tn = std::max(32, std::min(kTmax, (Tn + 31) & ~31));
     R = Tn * G;
     const int spb = Tn / 32;
-    int nbuf = env_int("B200_SPMV_PANEL_NBUF", 2) == 1 ? 1 : 2;
+    /* one wide x slice beats two narrower ones here: the per-panel cost (barrier, hand-over)
+     * outweighs the exposed slice load, 169 KB at ~216 GB/s per SM (profiles/r01_run47_sweep.txt) */
+    int nbuf = env_int("B200_SPMV_PANEL_NBUF", 1) == 2 ? 2 : 1;
     /* the stream lands in a shared-memory ring (S stages of K pair rows per warp), nothing
      * is left for the L1 to do, so the whole 227 KB is used */
     int ring_K = 0, ring_S = 0;

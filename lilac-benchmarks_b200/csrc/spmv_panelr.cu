@@ -222,8 +222,14 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
             if (sr == 0) mbar_wait(rb_w + slot, par);
             const int n = min(npair - kp, K - sr);
             const int ro = (slot * K + sr) * 32;
-            if (n == K) consume_rows<T, G, K, true>(rv_w + ro, rc_w + ro, n, xs, sums, st);
-            else        consume_rows<T, G, K, false>(rv_w + ro, rc_w + ro, n, xs, sums, st);
+            if (n == K) {
+                consume_rows<T, G, K, true>(rv_w + ro, rc_w + ro, n, xs, sums, st);
+            } else {
+                /* head / tail of a panel inside a stage: one pair row at a time (lean code
+                 * beats a predicated unrolled batch here) */
+                for (int u = 0; u < n; ++u)
+                    consume_rows<T, G, 1, true>(rv_w + ro + u * 32, rc_w + ro + u * 32, 1, xs, sums, st);
+            }
             kp += n;
             sr += n;
             if (sr == K) {                                /* stage consumed: refill its slot */

@@ -49,6 +49,10 @@ def lib():
         L.npb_csr_free.restype = None
         L.npb_cg_run.argtypes = [POINTER(CgClass), POINTER(Csr), c_void_p, POINTER(CgResult), c_int]
         L.npb_cg_run.restype = c_int
+        L.npb_time_spmv_calls.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double),
+                                          POINTER(POINTER(c_double)), c_int, POINTER(c_int),
+                                          POINTER(c_int), c_int, c_int]
+        L.npb_time_spmv_calls.restype = c_double
         L.npb_randlc.argtypes = [POINTER(c_double), c_double]
         L.npb_randlc.restype = c_double
         _lib = L
@@ -133,3 +137,15 @@ def run_cg(matrix, harness_addr, verbose=False):
     return {"zeta": res.zeta, "rnorm": res.rnorm, "err": res.err, "verified": bool(res.verified),
             "t_bench": res.t_bench, "t_init": res.t_init, "mops": res.mops,
             "spmv_calls": res.spmv_calls, "zeta_hist": zeta_hist, "rnorm_hist": rnorm_hist}
+
+
+def time_spmv_calls(harness_addr, ov, a, xs, rowstr, colidx, rows, calls):
+    """Seconds per ABI call measured by the C caller loop (callers/npb/cg.c,
+    npb_time_spmv_calls): `calls` products y = A x through the function at
+    `harness_addr`, x rotating over the numpy vectors `xs`."""
+    dp = POINTER(c_double)
+    xp = (dp * len(xs))(*[x.ctypes.data_as(dp) for x in xs])
+    sec = lib().npb_time_spmv_calls(harness_addr, ov.ctypes.data_as(dp), a.ctypes.data_as(dp), xp, len(xs),
+                                    rowstr.ctypes.data_as(POINTER(c_int)),
+                                    colidx.ctypes.data_as(POINTER(c_int)), int(rows), int(calls))
+    return sec / max(int(calls), 1)
