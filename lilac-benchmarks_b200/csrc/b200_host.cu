@@ -385,18 +385,18 @@ static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl)
 }
 
 /* modelled launch time of a ring plan against the SELL family, both fitted on NPB
- * class D row blocks (profiles/r01_run37_sweep.txt): the ring kernel streams ~4.6 TB/s
- * of stored entries and pays ~0.65 us per panel (barrier, x slice hand-over) in every
- * wave of CTAs; SELL is bound by the L1TEX wavefront rate of its gather,
- * ~1.29 clk per entry and SM. */
+ * class D row blocks (profiles/r01_run47_sweep.txt, r01_run48_sweep_ring_single_buffer.txt):
+ * the ring kernel streams ~5.5 TB/s of stored entries and pays ~1.4 us per panel
+ * (barrier, x slice hand-over and load) in every wave of CTAs; SELL is bound by the
+ * L1TEX wavefront rate of its gather, ~1.29 clk per entry and SM. */
 static bool panel_plan_beats_sell(const b200_matrix *m, const PanelPlan &pl)
 {
     const double es = (double)elem_size(m->dtype);
     const double nblk = (double)((m->rows + pl.R - 1) / pl.R);
-    const double stream = (double)m->nnz * (es + 2) * 1.09 + (double)m->rows * pl.P * 2;
+    const double stream = (double)m->nnz * (es + 2) * 1.06 + (double)m->rows * pl.P * 2;
     const double waves = std::ceil(nblk / g_sm_count);
-    const double t_panel = waves * (stream / (waves * 4.6e12) * std::max(1.0, waves * g_sm_count / nblk) +
-                                    pl.P * 0.65e-6);
+    const double per_panel = pl.nbuf == 1 ? 1.4e-6 : 0.65e-6;
+    const double t_panel = stream / 5.5e12 * std::max(1.0, waves * g_sm_count / nblk) + waves * pl.P * per_panel;
     const double t_sell = (double)m->nnz * 1.29 / (g_sm_count * 1.965e9);
     return t_panel < 0.92 * t_sell;
 }
