@@ -275,8 +275,8 @@ def run_b200(args, world, rank, local_rank):
 
         def step(i):
             (psh or sh).step(x_local)
-        # peer: push, flag wait, product, consumed; nccl: slot copy + product (+ the NCCL kernel)
-        launches_per_step = rm.launches_per_exec + (3 if psh is not None else 1)
+        # peer: exchange kernel + product; nccl: slot copy + product (+ the NCCL kernel)
+        launches_per_step = rm.launches_per_exec + 1
         y = (psh or sh).y_local
 
     B = algorithmic_bytes(nnz_global, n_global, ncols)

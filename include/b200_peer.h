@@ -61,6 +61,12 @@ void b200_peer_push(b200_peer_group *g, const double *v, int n_local, int64_t lo
  * products without a scalar exchange in between */
 void b200_peer_push_after(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
                           uint64_t e_consumed, void *stream);
+/* the whole exchange of one of a series of back-to-back products in ONE launch
+ * (epochs e = 1, 2, 3, ... on the stream that also runs the products): report
+ * epoch e - 1 as consumed, wait for every rank's report, push the slice, publish
+ * epoch e and retire only when every rank's epoch e has arrived */
+void b200_peer_exchange(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
+                        void *stream);
 /* report that this rank's product has consumed vector epoch e */
 void b200_peer_consumed(b200_peer_group *g, uint64_t e, void *stream);
 /* block until every rank has published epoch >= e on the vector flag */

@@ -147,6 +147,40 @@ peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
         for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
 }
 
+/* One launch per product for back-to-back products (b200_peer_exchange): report the
+ * previous vector (epoch e - 1) as consumed -- the product that read it precedes this
+ * kernel in the stream --, wait until every rank has done so, push the new slice,
+ * publish epoch e, and let the last block wait for everybody's epoch e, so that the
+ * kernel only retires once the whole vector is in this rank's buffer. */
+__global__ void __launch_bounds__(kThreads)
+peer_exchange_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e)
+{
+    if (e > 1) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            __threadfence_system();
+            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e - 1);
+        }
+        wait_flags(g.rflag[g.rank], g.nranks, e - 1);
+    }
+    const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    const int n2 = vec_ok ? n >> 1 : 0;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v);
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
+        const double2 val = v2[i];
+        for (int j = 0; j < g.nranks; ++j)
+            reinterpret_cast<double2 *>(g.xfull[j] + lo)[i] = val;
+    }
+    for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double val = v[i];
+        for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
+    }
+    if (last_block(g.counter + 0)) {
+        if (threadIdx.x == 0)
+            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+        wait_flags(g.vflag[g.rank], g.nranks, e);
+    }
+}
+
 __global__ void peer_wait_vector_kernel(PeerDev g, unsigned long long e)
 {
     wait_flags(g.vflag[g.rank], g.nranks, e);
@@ -343,6 +377,12 @@ extern "C" void b200_peer_push_after(b200_peer_group *g, const double *v, int n_
 {
     peer_push_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e,
                                                                      e_consumed);
+}
+
+extern "C" void b200_peer_exchange(b200_peer_group *g, const double *v, int n_local, int64_t lo,
+                                   uint64_t e, void *stream)
+{
+    peer_exchange_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e);
 }
 
 extern "C" void b200_peer_consumed(b200_peer_group *g, uint64_t e, void *stream)

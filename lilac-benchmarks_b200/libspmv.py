@@ -106,6 +106,7 @@ def lib():
     L.b200_peer_xfull.restype = c_void_p
     L.b200_peer_push.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, c_void_p]
     L.b200_peer_push_after.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, u64, c_void_p]
+    L.b200_peer_exchange.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, c_void_p]
     L.b200_peer_consumed.argtypes = [c_void_p, u64, c_void_p]
     L.b200_peer_wait_vector.argtypes = [c_void_p, u64, c_void_p]
     L.b200_peer_dot.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, u64, c_void_p]

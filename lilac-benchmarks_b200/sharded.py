@@ -349,8 +349,9 @@ class PeerNpbCg:
 class PeerShardedSpmv:
     """y_local = A[rows of this rank, :] @ x with the exchange done by this
     rank's own push kernel over NVLink peer memory (include/b200_peer.h) instead
-    of an NCCL allgather: push my slice into every rank's x buffer, wait for
-    everybody's flag, run the local kernel, report the buffer as consumed."""
+    of an NCCL allgather: one exchange kernel (report the previous vector as
+    consumed, wait for every rank's report, push my slice into every rank's x
+    buffer, publish, wait for everybody's flag), then the local kernel."""
 
     def __init__(self, libspmv_module, resident_matrix, layout, rank, dist=None, device="cuda"):
         import ctypes as C
@@ -378,13 +379,10 @@ class PeerShardedSpmv:
 
     def step(self, x_local):
         s = self.torch.cuda.current_stream().cuda_stream
-        prev = self.epoch
         self.epoch += 1
-        self.L.b200_peer_push_after(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo,
-                                    self.epoch, prev, s)
-        self.L.b200_peer_wait_vector(self.g, self.epoch, s)
+        # one launch: consumed(previous) -> wait -> push -> publish -> wait for everybody
+        self.L.b200_peer_exchange(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, self.epoch, s)
         self.rm.exec_ptr(self.xfull, self.y_local.data_ptr(), s)
-        self.L.b200_peer_consumed(self.g, self.epoch, s)
         return self.y_local
 
     def close(self):
