@@ -530,10 +530,17 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
                             cudaMemcpyHostToDevice, g_stream));
     const size_t nval = (size_t)run + 64;
-    CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
-    CUDA_OK(cudaMalloc((void **)&m->d_pcol, nval * sizeof(uint16_t)));
-    CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, g_stream));
-    CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
+    if (fmt == 2) {
+        /* one stream: per pair row 32 value pairs followed by 32 column pairs */
+        CUDA_OK(cudaMalloc(&m->d_pval, nval * (es + 2)));
+        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * (es + 2), 0, 64 * (es + 2), g_stream));
+        m->d_pcol = nullptr;
+    } else {
+        CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
+        CUDA_OK(cudaMalloc((void **)&m->d_pcol, nval * sizeof(uint16_t)));
+        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, g_stream));
+        CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
+    }
     DevPanel &pm = m->panel;
     pm.val = m->d_pval; pm.col = m->d_pcol; pm.meta = m->d_meta; pm.slice_off = m->d_slice_off;
     pm.rowids = reinterpret_cast<const uint16_t *>(m->d_meta);
@@ -546,10 +553,10 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     if (fmt == 2) {
         if (m->dtype == B200_F64)
             launch_panelg_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                       d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
+                                       d_seglen, (unsigned char *)m->d_pval, g_stream);
         else
             launch_panelg_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                      d_seglen, (float *)m->d_pval, m->d_pcol, g_stream);
+                                      d_seglen, (unsigned char *)m->d_pval, g_stream);
     } else if (m->dtype == B200_F64)
         launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
                                   d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);

@@ -61,7 +61,8 @@ void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s);
  * see spmv_panel.cu for the format.
  * ---------------------------------------------------------------------- */
 struct DevPanel {
-    const void     *val;        /* T[padded], tile-major SELL-pair order */
+    const void     *val;        /* fmt 0: T[padded], tile-major SELL-pair order; fmt 2: the unified stream,
+                                 * per pair row 32 value pairs then 32 column pairs (col unused) */
     const uint16_t *col;        /* u16[padded], 0-based column inside its panel; W = +0.0 slot */
     const ushort4  *meta;       /* fmt 0: [nblk * P * R/G]: {row A, row B, pair where B starts, 0} */
     const uint16_t *rowids;     /* fmt 2: [nblk * P * R]: the G tile-local row ids of every lane */
@@ -100,7 +101,7 @@ void launch_panelg_sort(const uint16_t *seglen, int ntiles, int R, int G, uint16
                         int *slice_elems, cudaStream_t s);
 template <typename T>
 void launch_panelg_fill(const T *val, const int *col, const int *rowptr, int rows,
-                        const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
+                        const DevPanel &pm, const uint16_t *seglen, unsigned char *stream_out,
                         cudaStream_t s);
 /* ... and its kernel: the matrix stream through per-warp shared-memory rings (spmv_panelr.cu) */
 template <typename T>

@@ -22,7 +22,9 @@
  *     extra entries on NPB class D), which puts the row switches of all
  *     lanes of a warp on the same pair;
  *   - slices are stored (row block, warp, panel)-major, so a warp's stream
- *     over all panels is one contiguous run of pair rows.
+ *     over all panels is one contiguous run of pair rows; a pair row is 32
+ *     value pairs followed by its 32 column pairs (640 bytes in fp64), so any
+ *     run of pair rows is one contiguous block of bytes.
  *
  * Padding entries are (+0.0, slot W) with slot W of the x slice holding +0.0:
  * they add +0.0 to a running sum that is never -0.0, i.e. change no bit.
@@ -94,8 +96,16 @@ __global__ void panelg_fill_kernel(const T *__restrict__ val, const int *__restr
                                    const uint16_t *__restrict__ seglen,
                                    const uint16_t *__restrict__ rowids,
                                    const int *__restrict__ slice_off, int nslices, int wmajor,
-                                   T *__restrict__ val_out, uint16_t *__restrict__ col_out)
+                                   unsigned char *__restrict__ stream_out)
 {
+    /* one pair row of a slice = 32 value pairs followed by 32 column pairs (kRowB bytes):
+     * a ring stage of K pair rows is then ONE contiguous block for ONE TMA bulk copy */
+    constexpr int kRowB = 32 * (2 * (int)sizeof(T) + 4);
+    auto put = [&](size_t pair_row, int lane_, int half, T v, uint16_t c) {
+        unsigned char *row = stream_out + pair_row * kRowB;
+        reinterpret_cast<T *>(row)[lane_ * 2 + half] = v;
+        reinterpret_cast<uint16_t *>(row + 64 * sizeof(T))[lane_ * 2 + half] = c;
+    };
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   /* global slice id */
     const int lane = threadIdx.x & 31;
     if (gw >= nslices) return;
@@ -126,28 +136,19 @@ __global__ void panelg_fill_kernel(const T *__restrict__ val, const int *__restr
                 const int mid = (lo + hi) >> 1;
                 if (col[mid] < c0) lo = mid + 1; else hi = mid;
             }
-            for (int e = 0; e < len; ++e, ++k) {
-                const size_t idx = (size_t)off + (size_t)(k >> 1) * 64 + lane * 2 + (k & 1);
-                val_out[idx] = val[lo + e];
-                col_out[idx] = (uint16_t)((col[lo + e] - c0) | (e == 0 ? 0x8000 : 0));
-            }
+            for (int e = 0; e < len; ++e, ++k)
+                put((size_t)(off >> 6) + (k >> 1), lane, k & 1, val[lo + e],
+                    (uint16_t)((col[lo + e] - c0) | (e == 0 ? 0x8000 : 0)));
         }
-        for (; k < k_end; ++k) {                                   /* +0.0 * x[W] = +0.0 */
-            const size_t idx = (size_t)off + (size_t)(k >> 1) * 64 + lane * 2 + (k & 1);
-            val_out[idx] = (T)0;
-            col_out[idx] = (uint16_t)W;
-        }
+        for (; k < k_end; ++k)                                     /* +0.0 * x[W] = +0.0 */
+            put((size_t)(off >> 6) + (k >> 1), lane, k & 1, (T)0, (uint16_t)W);
     }
-    for (; k < nent; ++k) {
-        const size_t idx = (size_t)off + (size_t)(k >> 1) * 64 + lane * 2 + (k & 1);
-        val_out[idx] = (T)0;
-        col_out[idx] = (uint16_t)W;
-    }
+    for (; k < nent; ++k) put((size_t)(off >> 6) + (k >> 1), lane, k & 1, (T)0, (uint16_t)W);
 }
 
 template <typename T>
 void launch_panelg_fill(const T *val, const int *col, const int *rowptr, int rows,
-                        const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
+                        const DevPanel &pm, const uint16_t *seglen, unsigned char *stream_out,
                         cudaStream_t s)
 {
     const int nslices = pm.nblk * pm.P * (pm.R / pm.G / 32);
@@ -155,11 +156,11 @@ void launch_panelg_fill(const T *val, const int *col, const int *rowptr, int row
     const long long threads = (long long)nslices * 32;
     panelg_fill_kernel<T><<<(int)((threads + 255) / 256), 256, 0, s>>>(
         val, col, rowptr, rows, pm.R, pm.G, pm.P, pm.W, seglen, pm.rowids, pm.slice_off, nslices,
-        pm.fmt == 2, val_out, col_out);
+        pm.fmt == 2, stream_out);
 }
 template void launch_panelg_fill<double>(const double *, const int *, const int *, int, const DevPanel &,
-                                         const uint16_t *, double *, uint16_t *, cudaStream_t);
+                                         const uint16_t *, unsigned char *, cudaStream_t);
 template void launch_panelg_fill<float>(const float *, const int *, const int *, int, const DevPanel &,
-                                        const uint16_t *, float *, uint16_t *, cudaStream_t);
+                                        const uint16_t *, unsigned char *, cudaStream_t);
 
 }  // namespace b200

@@ -15,8 +15,10 @@
  *     warp's stream over ALL panels of its row block is one contiguous run of
  *     pair rows (32 lanes x {value pair, column pair});
  *   - every warp owns a ring of S stages of K pair rows in shared memory and
- *     refills a stage with two TMA bulk copies (values, columns) as soon as
- *     it has consumed it; one mbarrier per stage.  Stages ignore panel
+ *     refills a stage with ONE TMA bulk copy as soon as it has consumed it
+ *     (a pair row holds its values and its columns side by side; the number
+ *     of bulk copies an SM can issue turned out to be the limit: K = 2 instead
+ *     of 4 pair rows per copy costs 40 %); one mbarrier per stage.  Stages ignore panel
  *     boundaries, so the bytes in flight are the ring size whatever the
  *     panel geometry;
  *   - the consumer is the flagged-stream consumer of spmv_panelg.cu: x slice
@@ -54,17 +56,19 @@ __device__ __forceinline__ void switch_row(LaneRows<T, G> &st, T *sums)
  * a slice (panelg_sort_kernel), so the flags of the 32 lanes fall on the same pair: one
  * warp vote per pair keeps the switch code off the common path. */
 template <typename T, int G, int K, bool FULL>
-__device__ __forceinline__ void consume_rows(const typename PairT<T>::type *rv, const uint32_t *rc,
+__device__ __forceinline__ void consume_rows(const unsigned char *rows, int lane,
                                              int n, const T *xs, T *sums, LaneRows<T, G> &st)
 {
-    typename PairT<T>::type v[K];
+    using P2 = typename PairT<T>::type;
+    constexpr int kRowB = 32 * ((int)sizeof(P2) + 4);     /* bytes of a pair row in the ring */
+    P2 v[K];
     uint32_t c[K];
     T xa[K], xb[K];
 #pragma unroll
     for (int u = 0; u < K; ++u) {
         if (FULL || u < n) {
-            v[u] = rv[u * 32];
-            c[u] = rc[u * 32];
+            v[u] = reinterpret_cast<const P2 *>(rows + u * kRowB)[lane];
+            c[u] = reinterpret_cast<const uint32_t *>(rows + u * kRowB + 32 * sizeof(P2))[lane];
         }
     }
 #pragma unroll
@@ -103,7 +107,7 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     const int spb = Tn >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = blockIdx.x;
-    /* layout: [x mbarriers 16 B][ring mbarriers spb*S*8][sums R+1][xbuf nbuf*(W+pad)][ring values][ring columns] */
+    /* layout: [x mbarriers 16 B][ring mbarriers spb*S*8][sums R+1][xbuf nbuf*(W+pad)][rings: spb*S*K pair rows] */
     uint64_t *xbars = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *rbars = reinterpret_cast<uint64_t *>(smem_raw + 16);
     const size_t soff = 16 + (size_t)spb * S * 8;
@@ -112,8 +116,7 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     const int WS = W + (16 / (int)sizeof(T));
     T *xbuf = reinterpret_cast<T *>(smem_raw + xoff);
     const size_t roff = (xoff + (size_t)nbuf * WS * sizeof(T) + 127) & ~(size_t)127;
-    P2 *ring_val = reinterpret_cast<P2 *>(smem_raw + roff);
-    uint32_t *ring_col = reinterpret_cast<uint32_t *>(smem_raw + roff + (size_t)spb * S * K * 32 * sizeof(P2));
+    constexpr int kRowB = 32 * ((int)sizeof(P2) + 4);     /* a pair row: 32 value pairs + 32 column pairs */
 
     for (int i = tid; i <= R; i += Tn) sums[i] = (T)0;
     if (tid == 0) {
@@ -132,20 +135,17 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     const int off0 = __ldg(woff);
     const int total = (__ldg(woff + P) - off0) >> 6;
     const int nstage = (total + K - 1) / K;
-    const P2 *gval = reinterpret_cast<const P2 *>(val) + (off0 >> 1);
-    const uint32_t *gcol = reinterpret_cast<const uint32_t *>(col) + (off0 >> 1);
-    P2 *rv_w = ring_val + (size_t)warp * S * K * 32 + lane;
-    uint32_t *rc_w = ring_col + (size_t)warp * S * K * 32 + lane;
+    const unsigned char *gstream = reinterpret_cast<const unsigned char *>(val) + (size_t)(off0 >> 6) * kRowB;
+    unsigned char *ring_w = smem_raw + roff + (size_t)warp * S * K * kRowB;
     uint64_t *rb_w = rbars + warp * S;
 
     auto issue_stage = [&](int t, int slot) {            /* lane 0: stage t -> slot t % S */
         const int r0 = t * K;
         const int nr = min(K, total - r0);
-        const uint32_t bv = (uint32_t)(nr * 32 * sizeof(P2)), bc = (uint32_t)(nr * 32 * 4);
+        const uint32_t bytes = (uint32_t)(nr * kRowB);     /* one copy: values and columns together */
         uint64_t *bar = rb_w + slot;
-        mbar_expect_tx(bar, bv + bc);
-        tma_bulk_g2s(rv_w - lane + (size_t)slot * K * 32, gval + (size_t)r0 * 32, bv, bar);
-        tma_bulk_g2s(rc_w - lane + (size_t)slot * K * 32, gcol + (size_t)r0 * 32, bc, bar);
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(ring_w + (size_t)slot * K * kRowB, gstream + (size_t)r0 * kRowB, bytes, bar);
     };
     if (lane == 0)
         for (int t = 0; t < S && t < nstage; ++t) issue_stage(t, t);
@@ -221,14 +221,14 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         while (kp < npair) {                              /* warp-uniform control flow */
             if (sr == 0) mbar_wait(rb_w + slot, par);
             const int n = min(npair - kp, K - sr);
-            const int ro = (slot * K + sr) * 32;
+            const unsigned char *rows_at = ring_w + (size_t)(slot * K + sr) * kRowB;
             if (n == K) {
-                consume_rows<T, G, K, true>(rv_w + ro, rc_w + ro, n, xs, sums, st);
+                consume_rows<T, G, K, true>(rows_at, lane, n, xs, sums, st);
             } else {
                 /* head / tail of a panel inside a stage: one pair row at a time (lean code
                  * beats a predicated unrolled batch here) */
                 for (int u = 0; u < n; ++u)
-                    consume_rows<T, G, 1, true>(rv_w + ro + u * 32, rc_w + ro + u * 32, 1, xs, sums, st);
+                    consume_rows<T, G, 1, true>(rows_at + u * kRowB, lane, 1, xs, sums, st);
             }
             kp += n;
             sr += n;
