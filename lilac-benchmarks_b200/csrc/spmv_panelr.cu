@@ -233,11 +233,10 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
             kp += n;
             sr += n;
             if (sr == K) {                                /* stage consumed: refill its slot */
+                /* every lane has used its values of the stage (they fed arithmetic), so the
+                 * slot can be overwritten: same hand-over as an "empty" mbarrier arrive */
                 __syncwarp();
-                if (lane == 0 && t_cur + S < nstage) {
-                    fence_proxy_async();
-                    issue_stage(t_cur + S, slot);
-                }
+                if (lane == 0 && t_cur + S < nstage) issue_stage(t_cur + S, slot);
                 ++t_cur;
                 sr = 0;
                 if (++slot == S) { slot = 0; par ^= 1u; }
