@@ -329,7 +329,9 @@ static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl)
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
     const size_t es = elem_size(m->dtype);
-    const int kRmax = 4096, kMaxPanels = 512;
+    /* up to 256 panels: NPB class D blocks need 71; class E blocks (9 M columns, 426 panels,
+     * 1.6 entries per (row, panel)) are left on the SELL path they were measured on */
+    const int kRmax = 4096, kMaxPanels = 256;
     const int kTmax = std::max(64, std::min(768, env_int("B200_SPMV_PANEL_TMAX", 512)));
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) {

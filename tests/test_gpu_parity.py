@@ -164,8 +164,8 @@ def test_ring_panel_kernel_bit_exact_on_sorted_rows(libspmv, oracle, dtype, shap
     a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=True)
     y0 = oracle.spmv(a, x, rowstr, c)
     env = dict(panel_env, B200_SPMV_PANEL_FMT=2)
-    if shape["ncols"] > 500 * env.get("B200_SPMV_PANEL_COLS", shape["ncols"]):
-        del env["B200_SPMV_PANEL_COLS"]          # more than 512 panels: the plan is refused
+    if shape["ncols"] > 250 * env.get("B200_SPMV_PANEL_COLS", shape["ncols"]):
+        del env["B200_SPMV_PANEL_COLS"]          # more than 256 panels: the plan is refused
     m, y = _exec_resident(libspmv, a, x, rowstr, c, "panel", env)
     if len(c):
         assert m.kernel_name == "panel", (m.kernel_name, m.ncols, m.nnz)

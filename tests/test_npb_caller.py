@@ -63,3 +63,18 @@ def test_makea_in_pieces_is_identical(npb):
     assert parts.n == whole.n and parts.nnz == whole.nnz
     assert np.array_equal(parts.rowstr, whole.rowstr)
     assert np.array_equal(parts.colidx, whole.colidx) and np.array_equal(parts.a, whole.a)
+
+
+def test_c_caller_loop_issues_the_calls(npb, oracle):
+    """npb_time_spmv_calls (the loop bench.py times the ABI with): every call
+    goes through the given function pointer with x rotating over the caller
+    vectors, y lands in ov, and the time per call is positive."""
+    m = npb.NpbMatrix("S")
+    rng = np.random.default_rng(3)
+    xs = [rng.standard_normal(m.n + 2) for _ in range(3)]
+    y = np.full(m.n, np.nan)
+    for calls in (1, 2, 3, 7):
+        sec = npb.time_spmv_calls(oracle.harness_address(), y, m.a, xs, m.rowstr, m.colidx, m.n, calls)
+        assert sec > 0.0
+        # the last call used xs[(calls - 1) % 3]
+        assert np.array_equal(y, oracle.spmv(m.a, xs[(calls - 1) % 3], m.rowstr, m.colidx))
