@@ -94,6 +94,11 @@ __device__ __forceinline__ void consume_rows(const unsigned char *rows, int lane
     }
 }
 
+#ifndef B200_XCOPY_BYTES
+#define B200_XCOPY_BYTES 262144
+#endif
+constexpr uint32_t kXCopyBytes = B200_XCOPY_BYTES;      /* largest single bulk copy of an x slice */
+
 template <typename T, int G, int K, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
@@ -163,8 +168,10 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         uint32_t left = (uint32_t)(cw_al * sizeof(T));
         const char *src = reinterpret_cast<const char *>(x + cbase);
         char *d = reinterpret_cast<char *>(dst);
+        /* few, large copies: issuing a bulk copy costs the issuing warp ~15 instructions and
+         * that warp is on everybody's critical path at the panel barrier */
         while (left) {
-            const uint32_t n = left > 32768u ? 32768u : left;
+            const uint32_t n = left > kXCopyBytes ? kXCopyBytes : left;
             tma_bulk_g2s(d, src, n, bar);
             d += n; src += n; left -= n;
         }
