@@ -397,8 +397,8 @@ def run_b200(args, world, rank, local_rank):
                         else "allgather of x per step (NCCL)"),
                        "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                        "same_workload_on_one_gpu": None if (world == 1 or workload != "D") else {
-                           "ms_per_step": 1.6313, "value": 5126.4, "unit": UNIT,
-                           "source": "profiles/r01_run48_sweep_ring_single_buffer.txt (class D, ring PANEL "
+                           "ms_per_step": 1.5457, "value": 5410.5, "unit": UNIT,
+                           "source": "profiles/r01_run58_sweep_register_staged_x.txt (class D, ring PANEL "
                                      "kernel, 1xB200; SELL kernel: 2.738 ms)"},
                        "gen_s": round(t_gen, 2), "upload_s": round(t_upload, 3)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
