@@ -161,8 +161,10 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
         constexpr int VE = 16 / sizeof(T);
         const int cw_al = cw & ~(VE - 1);
-        for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);   /* ragged tail */
-        fence_proxy_async();
+        if (cw_al < cw) {                                 /* ragged tail: generic stores, then the fence */
+            for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);
+            fence_proxy_async();
+        }
         uint64_t *bar = &xbars[p & (nbuf - 1)];
         mbar_expect_tx(bar, (uint32_t)(cw_al * sizeof(T)));
         uint32_t left = (uint32_t)(cw_al * sizeof(T));
@@ -198,6 +200,12 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     int sr = 0;             /* pair rows of the stage already consumed */
 
     for (int p = 0; p < P; ++p) {
+        /* first thing after the barrier: request the x slice (thread 0's warp is on
+         * everybody's critical path, so nothing is queued in front of the request) */
+        if (use_tma && tid == 0) {
+            if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
+            if (nbuf == 1 && p > 0) issue_panel(p);
+        }
         LaneRows<T, G> st;
         st.ids = ids_next;
         if (p + 1 < P) ids_next = load_ids<G>(my_ids + (size_t)(p + 1) * Tn * G);
@@ -206,10 +214,6 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         if (p + 1 < P) o_nxt = __ldg(woff + p + 2);
 
         if (use_tma) {
-            if (tid == 0) {
-                if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
-                if (nbuf == 1 && p > 0) issue_panel(p);
-            }
             mbar_wait(&xbars[p & (nbuf - 1)], (uint32_t)((p >> (nbuf - 1)) & 1));
         } else {
             if (nbuf == 2 && p + 1 < P) coop_panel(p + 1);
