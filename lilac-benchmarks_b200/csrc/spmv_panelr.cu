@@ -1,11 +1,11 @@
 /*
  * spmv_panelr.cu -- PANEL with the matrix stream in a shared-memory ring
- * ("ring kernel", DevPanel::fmt == 2).
+ * ("ring kernel", DevPanel::fmt == 2; layout built by spmv_panelg.cu).
  *
- * What limits the register-staged PANEL kernels on wide matrices (NPB class D
- * row blocks: ~110 panels, ~4 entries per (row, panel)) is how much of the
- * matrix stream is in flight: a lane holds two chunks of U pairs, every panel
- * is walked in whole chunks, so with a few pairs per lane and panel the
+ * What limits a register-staged PANEL kernel on wide matrices (NPB class D
+ * row blocks: ~70-140 panels, 4-7 entries per (row, panel)) is how much of
+ * the matrix stream is in flight: a lane holds two chunks of U pairs, every
+ * panel is walked in whole chunks, so with a few pairs per lane and panel the
  * prefetch reaches one panel ahead (~48 KB per SM), and the loads in flight
  * also need L1 lines, which the x slices in shared memory take away
  * (profiles/r01_run28, r01_run29).  Here the stream never touches registers
@@ -13,18 +13,20 @@
  *
  *   - the slices are stored warp-major -- (row block, warp, panel) -- so a
  *     warp's stream over ALL panels of its row block is one contiguous run of
- *     pair rows (32 lanes x {value pair, column pair});
+ *     pair rows; a pair row is 32 value pairs followed by its 32 column pairs
+ *     (640 bytes in fp64);
  *   - every warp owns a ring of S stages of K pair rows in shared memory and
- *     refills a stage with ONE TMA bulk copy as soon as it has consumed it
- *     (a pair row holds its values and its columns side by side; the number
- *     of bulk copies an SM can issue turned out to be the limit: K = 2 instead
- *     of 4 pair rows per copy costs 40 %); one mbarrier per stage.  Stages ignore panel
- *     boundaries, so the bytes in flight are the ring size whatever the
- *     panel geometry;
- *   - the consumer is the flagged-stream consumer of spmv_panelg.cu: x slice
- *     of the panel in shared memory (TMA, double-buffered), bit 15 of a
- *     column starts a new row of the lane, running sums parked in shared
- *     memory, separately rounded multiply and add in the reference's order
+ *     refills a stage with ONE TMA bulk copy as soon as it has consumed it,
+ *     one mbarrier per stage (the number of bulk copies an SM issues matters:
+ *     K = 2 instead of 4 pair rows per copy costs 20 %, a second copy per
+ *     stage 3 %).  Stages ignore panel boundaries, so the bytes in flight are
+ *     the ring size whatever the panel geometry;
+ *   - the consumer: x slice of the panel in shared memory (TMA; one wide
+ *     slice by default, two with nbuf = 2), bit 15 of a column starts a new
+ *     row of the lane -- on the same pair in all 32 lanes, so one warp vote
+ *     per pair keeps the switch code off the common path --, running sums
+ *     parked in shared memory with the next row's sum pre-loaded, separately
+ *     rounded multiply and add in the reference's order
  *     (libspmv/native-impl.c:1-12) => bit-identical results for sorted rows.
  */
 #include "panel_common.cuh"
