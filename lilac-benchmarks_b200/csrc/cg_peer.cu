@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kBlocks = 296;
 constexpr int kThreads = 256;
+static_assert(kBlocks <= 2 * kThreads, "publish_scalar reduces two partials per thread at most");
 constexpr int NR = B200_PEER_MAX_RANKS;
 
 #define PEER_OK(call)                                                          \
@@ -109,15 +110,26 @@ __device__ __forceinline__ double slot_sum(const PeerDev &g, int slot)
     return t;
 }
 
-/* the last block reduces the block partials in fixed order and publishes */
+/* the last block reduces the block partials in a fixed order -- pairs kThreads apart, an
+ * xor-shuffle tree, the warp sums left to right; the whole block takes part, one thread
+ * adding 296 values cost ~6 us per scalar -- and publishes the sum to every rank */
 __device__ __forceinline__ void publish_scalar(const PeerDev &g, int slot, unsigned long long e,
                                                unsigned int *counter)
 {
-    if (last_block(counter)) {
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) t += g.partial[b];
-            for (int j = 0; j < g.nranks; ++j) g.scal[j][slot * NR + g.rank] = t;
+    __shared__ double wsum[kThreads / 32];
+    if (last_block(counter)) {                           /* block-uniform */
+        const int t = threadIdx.x, nb = (int)gridDim.x;  /* nb <= 2 * kThreads */
+        double v = t < nb ? g.partial[t] : 0.0;
+        if (t + kThreads < nb) v += g.partial[t + kThreads];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) wsum[t >> 5] = v;
+        __syncthreads();
+        if (t == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) tot += wsum[w];
+            for (int j = 0; j < g.nranks; ++j) g.scal[j][slot * NR + g.rank] = tot;
             __threadfence_system();
             for (int j = 0; j < g.nranks; ++j) st_release_sys(g.sflag[j] + slot * NR + g.rank, e);
         }
