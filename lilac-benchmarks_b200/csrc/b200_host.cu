@@ -323,7 +323,7 @@ struct PanelPlan { int P, W, R, G, nbuf, fmt, ring_K, ring_S; };
  * wide matrices.  One CTA per SM and as few passes over x as the shared-memory
  * budget (R + 1 running sums) allows; the rest of the 227 KB holds the per-warp
  * rings of the matrix stream and two x slices. */
-static bool panel_plan_flagged(const b200_matrix *m, PanelPlan *pl)
+static bool panel_plan_ring(const b200_matrix *m, PanelPlan *pl)
 {
     const int fmt = 2;
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
@@ -469,7 +469,7 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     if (!ok && want_fmt != 0) {
         /* wide matrices: tall row blocks, G rows per lane (spmv_panelg.cu) */
         PanelPlan pl;
-        if (panel_plan_flagged(m, &pl) && (forced || panel_plan_beats_sell(m, pl))) {
+        if (panel_plan_ring(m, &pl) && (forced || panel_plan_beats_sell(m, pl))) {
             P = pl.P; W = pl.W; R = pl.R; G = pl.G; nbuf = pl.nbuf; fmt = pl.fmt;
             ring_K = pl.ring_K; ring_S = pl.ring_S;
             ok = true;

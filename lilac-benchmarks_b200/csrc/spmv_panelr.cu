@@ -103,7 +103,7 @@ constexpr uint32_t kXCopyBytes = B200_XCOPY_BYTES;      /* largest single bulk c
 
 template <typename T, int G, int K, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
+spmv_panelr_kernel(const unsigned char *__restrict__ stream,
                    const uint16_t *__restrict__ rowids, const int *__restrict__ slice_off,
                    const T *__restrict__ x, T *__restrict__ y,
                    int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S)
@@ -142,7 +142,7 @@ spmv_panelr_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     const int off0 = __ldg(woff);
     const int total = (__ldg(woff + P) - off0) >> 6;
     const int nstage = (total + K - 1) / K;
-    const unsigned char *gstream = reinterpret_cast<const unsigned char *>(val) + (size_t)(off0 >> 6) * kRowB;
+    const unsigned char *gstream = stream + (size_t)(off0 >> 6) * kRowB;
     unsigned char *ring_w = smem_raw + roff + (size_t)warp * S * K * kRowB;
     uint64_t *rb_w = rbars + warp * S;
 
@@ -291,7 +291,7 @@ static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t
     const size_t smem = panelr_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panelr_kernel<T, G, K, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
-        static_cast<const T *>(pm.val), pm.col, pm.rowids, pm.slice_off, x, y,
+        static_cast<const unsigned char *>(pm.val), pm.rowids, pm.slice_off, x, y,
         pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S);
 }
 
