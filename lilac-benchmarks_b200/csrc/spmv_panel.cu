@@ -290,8 +290,10 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
         constexpr int VE = 16 / sizeof(T);
         const int cw_al = cw & ~(VE - 1);
-        for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);   /* ragged tail */
-        fence_proxy_async();
+        if (cw_al < cw) {                                 /* ragged tail: generic stores, then the fence */
+            for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);
+            fence_proxy_async();
+        }
         uint64_t *bar = &bars[p & (nbuf - 1)];
         if (cw_al > 0) {
             mbar_expect_tx(bar, (uint32_t)(cw_al * sizeof(T)));
@@ -334,19 +336,21 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);
 
     for (int p = 0; p < P; ++p) {
+        /* double buffer: slot (p+1)&1 was released by the barrier that ended
+         * panel p-1, so panel p+1 is requested while panel p is computed.
+         * single buffer (wide panels): panel p is requested here, after the
+         * barrier that ended panel p-1.  The request comes first: thread 0's
+         * warp is on everybody's critical path at the next barrier, and the
+         * proxy fence of a ragged tail would wait for any load queued before it. */
+        if (use_tma && tid == 0) {
+            if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
+            if (nbuf == 1 && p > 0) issue_panel(p);
+        }
         const ushort4 mt = mt_next;
         if (p + 1 < P) mt_next = meta[((size_t)rb * P + p + 1) * Tn + tid];
         const int npair = s_slice[p * spb + warp].y;
 
-        /* double buffer: slot (p+1)&1 was released by the barrier that ended
-         * panel p-1, so panel p+1 is requested while panel p is computed.
-         * single buffer (wide panels): panel p is requested here, after the
-         * barrier that ended panel p-1. */
         if (use_tma) {
-            if (tid == 0) {
-                if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
-                if (nbuf == 1 && p > 0) issue_panel(p);
-            }
             mbar_wait(&bars[p & (nbuf - 1)], (uint32_t)((p >> (nbuf - 1)) & 1));
         } else {
             if (nbuf == 2 && p + 1 < P) coop_panel(p + 1);
