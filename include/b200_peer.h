@@ -67,6 +67,17 @@ void b200_peer_push_after(b200_peer_group *g, const double *v, int n_local, int6
  * epoch e and retire only when every rank's epoch e has arrived */
 void b200_peer_exchange(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
                         void *stream);
+/* The exchange half of a product that waits for its x slices itself
+ * (b200_spmv_exec_sliced): epochs e = 1, 2, 3, ... alternate between two vector buffers
+ * (b200_peer_xbuf(g, e)); report epoch e - 1 as consumed, wait for every rank's report of
+ * e - 2 (a whole step old: a slow rank does not hold the others back), push the slice,
+ * publish epoch e on the vector flags (b200_peer_vflags).  Does not wait for arrivals. */
+void b200_peer_post(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
+                    void *stream);
+/* the local full-length vector of epoch e, and this rank's row of vector flags
+ * (flag[r] >= e: the slice of rank r of epoch e has arrived); device pointers */
+double *b200_peer_xbuf(b200_peer_group *g, uint64_t e);
+const unsigned long long *b200_peer_vflags(b200_peer_group *g);
 /* report that this rank's product has consumed vector epoch e */
 void b200_peer_consumed(b200_peer_group *g, uint64_t e, void *stream);
 /* block until every rank has published epoch >= e on the vector flag */

@@ -72,8 +72,11 @@ enum {
 
 enum { B200_F64 = 0, B200_F32 = 1 };
 
-/* Select / initialise the device (-1 = keep cudaGetDevice()).  Optional: every
- * entry point initialises lazily, as dlopen callers need (pagerank/main.cpp:19). */
+/* Select / initialise the device of the drop-in path (-1 = keep cudaGetDevice()).
+ * Optional: every entry point initialises lazily, as dlopen callers need
+ * (pagerank/main.cpp:19).  b200_spmv_upload / _upload_device build on the device that
+ * is current when they are called; exec / release switch to the matrix's device and
+ * restore the caller's, so one process can hold matrices on several GPUs. */
 int b200_spmv_init(int device);
 
 /* Upload a 1-based CSR row block from HOST arrays and keep it resident.
@@ -90,6 +93,22 @@ void b200_spmv_release(b200_matrix *m);
  * d_x must hold at least b200_spmv_ncols(m) elements.  Asynchronous. */
 int b200_spmv_exec(b200_matrix *m, const void *d_x, void *d_y, void *stream);
 
+/* The same on x that is still being assembled from the slices of `nranks` GPUs
+ * (include/b200_peer.h): flags[r] >= epoch <=> columns [r * cols_per_rank, (r + 1) *
+ * cols_per_rank) are in d_x.  The kernel waits per slice, just before the panels that
+ * need it, so the product overlaps the exchange.  Returns -1 without launching when the
+ * matrix's kernel family cannot do that (wait for the vector first, then b200_spmv_exec). */
+int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y, void *stream,
+                          const unsigned long long *flags, unsigned long long epoch,
+                          int cols_per_rank, int nranks);
+
+/* Upload from DEVICE arrays of the current device (same 1-based contents as the ABI;
+ * the on-device NPB generator produces them): no PCIe traffic. */
+b200_matrix *b200_spmv_upload_device(const void *d_a, const int *d_rowstr, const int *d_colidx,
+                                     int rows, int dtype, int kernel);
+
+int         b200_spmv_device(const b200_matrix *m);  /* device the matrix lives on */
+int         b200_spmv_waits_in_kernel(const b200_matrix *m);  /* 1: b200_spmv_exec_sliced works */
 int         b200_spmv_rows(const b200_matrix *m);
 int         b200_spmv_ncols(const b200_matrix *m);   /* max(colidx) */
 int64_t     b200_spmv_nnz(const b200_matrix *m);
@@ -111,8 +130,19 @@ void b200_spmv_row_histogram(const b200_matrix *m, int64_t bins[32],
  * parts+1 boundaries into `bounds` so that every part holds ~nnz/parts. */
 void b200_spmv_partition_rows(const int *rowstr, int rows, int parts, int *bounds);
 
-/* Resident cache of the drop-in symbols */
+/* Resident cache of the drop-in symbols.
+ *
+ * Staleness: like libspmv/gpu.c:140-262 the host pages of a resident matrix are
+ * write-protected and a write to them drops the device copy (B200_SPMV_GUARD=0 turns
+ * that off; then only the sampled per-call fingerprint notices a change).  What
+ * neither can see -- arrays freed and mapped again at the same addresses with other
+ * contents of the same shape -- MUST be announced with b200_spmv_invalidate().
+ *
+ * Several devices: B200_SPMV_DEVICES="0,1,2,3" (or "all") makes the drop-in symbols
+ * spread every matrix of at least B200_SPMV_MULTI_MIN_NNZ (default 4 Mi) nonzeros over
+ * those GPUs in nnz-balanced row blocks; callers are unchanged. */
 void b200_spmv_invalidate(void);   /* forget every cached matrix (host arrays changed) */
+int  b200_spmv_devices_in_use(void);   /* most devices any cached matrix is spread over */
 
 typedef struct {
     uint64_t calls;            /* ABI calls served */

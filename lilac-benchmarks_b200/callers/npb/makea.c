@@ -143,6 +143,26 @@ static int make_vectors(const npb_cg_class *c)
     return 0;
 }
 
+/* the generating vectors and the size_i sequence (cg.f:876: size = size * ratio), for a
+ * generator that assembles the rows elsewhere (include/b200_npb.h: on the device) */
+int npb_vectors_get(const npb_cg_class *c, const int **arow, const int **acol, const double **aelt,
+                    double **size_out)
+{
+    if (make_vectors(c)) return -3;
+    *arow = g_vec.arow; *acol = g_vec.acol; *aelt = g_vec.aelt;
+    if (size_out) {
+        double *sz = (double *)malloc(sizeof(double) * (size_t)c->na);
+        if (!sz) return -3;
+        double size = 1.0;
+        const double ratio = pow(c->rcond, 1.0 / (double)c->na);
+        for (int i = 0; i < c->na; ++i) { sz[i] = size; size = size * ratio; }
+        *size_out = sz;                         /* caller frees with npb_free */
+    }
+    return 0;
+}
+
+void npb_free(void *p) { free(p); }
+
 void npb_makea_release_cache(void)
 {
     free(g_vec.arow); free(g_vec.acol); free(g_vec.aelt);

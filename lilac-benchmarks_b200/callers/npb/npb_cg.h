@@ -52,6 +52,13 @@ int  npb_makea_rows(const npb_cg_class *c, int row_lo, int row_hi, npb_csr *out)
 /* the generating vectors of the last class are cached between calls (several
  * row blocks of one class replay the random stream once); this drops them */
 void npb_makea_release_cache(void);
+/* The n generating sparse vectors of the class (cached like above) and a malloc'ed copy of
+ * the size_i sequence (free with npb_free): the sequential part of makea, for a generator
+ * that assembles the rows elsewhere (include/b200_npb.h does it on the GPU).
+ * arow[n], acol / aelt [n * (nonzer + 1)]. */
+int  npb_vectors_get(const npb_cg_class *c, const int **arow, const int **acol, const double **aelt,
+                     double **size_out);
+void npb_free(void *p);
 
 typedef struct {
     double zeta;            /* final zeta */

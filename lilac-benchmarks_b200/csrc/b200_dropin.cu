@@ -1,0 +1,735 @@
+/*
+ * b200_dropin.cu -- host layer of libb200-spmv.so, part 2: the libspmv ABI
+ * (spmv_harness_ / f_spmv_harness_) on top of the resident-matrix layer of
+ * b200_host.cu.
+ *
+ * Reference behaviour mirrored (and where it deliberately differs):
+ *   libspmv/gpu.c:227-262  matrix kept resident, keyed by the host pointers;
+ *                          here the key also carries rows and nnz, and several
+ *                          matrices can be resident at once (LRU).
+ *   libspmv/gpu.c:140-209  mprotect/SIGSEGV invalidation: ON by default like the
+ *                          reference's (B200_SPMV_GUARD=0 switches it off), but
+ *                          only pages lying entirely inside the arrays are
+ *                          protected and a previously installed handler is
+ *                          chained to.  Second line of defence, for what the
+ *                          guard cannot see (arrays smaller than a page, memory
+ *                          freed and mapped again): a content fingerprint
+ *                          checked on every call (B200_SPMV_VALIDATE=0: off) and
+ *                          b200_spmv_invalidate().
+ *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but pinned caller
+ *                          vectors are read / written in place over PCIe by the
+ *                          kernels, pageable ones go through pinned bounce buffers
+ *                          filled by a small pool of copy threads.
+ *   single device          gpu.c drives one GPU.  With B200_SPMV_DEVICES=0,1,..
+ *                          (or "all") the SAME two symbols drive several: the rows
+ *                          are split into nnz-balanced blocks, one per device;
+ *                          per call every device pulls 1/G of x over its own PCIe
+ *                          link and stores it into every device's x buffer over
+ *                          NVLink (one kernel: PCIe read, G peer stores), runs
+ *                          its block's product and writes its y block back
+ *                          (SURVEY.md 8e "ABI mode").  One process, peer access
+ *                          between the devices, no collective library.
+ */
+#include "host_internal.h"
+
+#include <signal.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+using namespace b200;
+
+/* ------------------------------------------------------------------------
+ * state
+ * ---------------------------------------------------------------------- */
+struct Part {
+    DevCtx *ctx;
+    b200_matrix *m;            /* rows [row_lo, row_hi); NULL when the block is empty */
+    int row_lo, row_hi;
+    size_t x_lo, x_hi;         /* byte range of x this device pulls from the host */
+    char *d_x, *d_y;           /* full-length x, this block's y */
+};
+
+struct CacheEntry {
+    const void *a; const int *rowstr; const int *colidx;
+    int rows; int64_t nnz; int dtype;
+    uint64_t fingerprint;
+    std::vector<uint64_t> win_hash;   /* hash of every window of a / colidx, taken at upload */
+    size_t win_next;                  /* window re-hashed by the next call */
+    uint64_t last_use;
+    int guard_slot;            /* index into g_guards, -1 when unguarded */
+    int nparts;
+    Part part[kMaxDevices];
+    int ncols;
+    void *h_x, *h_y;           /* pinned bounce buffers (portable, mapped) */
+    size_t x_bytes, y_bytes;
+};
+
+struct PinnedRange { char *lo, *hi; };
+
+static std::vector<CacheEntry> g_cache;
+static std::vector<PinnedRange> g_pinned;
+static uint64_t g_tick = 0;
+static b200_spmv_stats g_stats;
+static bool g_conf_ready = false;
+static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 1;
+static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
+static int g_ndev = 0, g_devs[kMaxDevices];
+static int64_t g_multi_min_nnz = 1 << 22;
+
+/* ------------------------------------------------------------------------
+ * Write guard (libspmv/gpu.c:140-209, ALIGN macro :204-209): the host pages of a
+ * resident matrix are made read-only and a SIGSEGV handler invalidates the
+ * cache entry when the caller writes to them, chaining to any handler that was
+ * installed before (gpu.c:180-181).  Differences: only pages lying entirely
+ * inside an array are protected (gpu.c rounds outwards, so a write to a
+ * neighbouring variable on a shared page silently drops the protection -- in
+ * NPB `x` follows `a` in COMMON), and several matrices can be guarded.
+ * The handler only touches this fixed table (async-signal-safe).
+ * ---------------------------------------------------------------------- */
+struct GuardRange { char *lo, *hi; };
+struct GuardSlot {
+    volatile int used;         /* 1 while a cache entry owns the slot */
+    volatile int tripped;      /* set by the handler: host copy was written */
+    GuardRange r[3];
+};
+static const int kMaxGuards = 16;
+static GuardSlot g_guards[kMaxGuards];
+static struct sigaction g_old_segv;
+static bool g_guard_installed = false;
+
+static void guard_handler(int sig, siginfo_t *si, void *ctx)
+{
+    char *addr = (char *)si->si_addr;
+    for (int k = 0; k < kMaxGuards; ++k) {
+        GuardSlot &g = g_guards[k];
+        if (!g.used) continue;
+        for (int j = 0; j < 3; ++j) {
+            if (g.r[j].lo && addr >= g.r[j].lo && addr < g.r[j].hi) {
+                for (int q = 0; q < 3; ++q)
+                    if (g.r[q].lo && g.r[q].hi > g.r[q].lo)
+                        mprotect(g.r[q].lo, (size_t)(g.r[q].hi - g.r[q].lo), PROT_READ | PROT_WRITE);
+                g.tripped = 1;
+                return;                           /* the faulting store is retried */
+            }
+        }
+    }
+    /* not ours: chain (gpu.c:180-181) or fall back to the default action */
+    if ((g_old_segv.sa_flags & SA_SIGINFO) && g_old_segv.sa_sigaction) {
+        g_old_segv.sa_sigaction(sig, si, ctx);
+    } else if (g_old_segv.sa_handler != SIG_DFL && g_old_segv.sa_handler != SIG_IGN &&
+               g_old_segv.sa_handler) {
+        g_old_segv.sa_handler(sig);
+    } else {
+        signal(SIGSEGV, SIG_DFL);
+    }
+}
+
+static GuardRange inner_pages(const void *p, size_t bytes)
+{
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGE_SIZE);
+    uintptr_t lo = ((uintptr_t)p + page - 1) / page * page;
+    uintptr_t hi = ((uintptr_t)p + bytes) / page * page;
+    GuardRange r = {nullptr, nullptr};
+    if (hi > lo) { r.lo = (char *)lo; r.hi = (char *)hi; }
+    return r;
+}
+
+static int guard_arm(const void *a, size_t a_bytes, const int *rowstr, size_t r_bytes,
+                     const int *colidx, size_t c_bytes)
+{
+    if (!g_guard) return -1;
+    if (!g_guard_installed) {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof sa);
+        sa.sa_flags = SA_SIGINFO;
+        sigemptyset(&sa.sa_mask);
+        sa.sa_sigaction = guard_handler;
+        if (sigaction(SIGSEGV, &sa, &g_old_segv) != 0) return -1;
+        g_guard_installed = true;
+    }
+    for (int k = 0; k < kMaxGuards; ++k) {
+        GuardSlot &g = g_guards[k];
+        if (g.used) continue;
+        g.r[0] = inner_pages(a, a_bytes);
+        g.r[1] = inner_pages(rowstr, r_bytes);
+        g.r[2] = inner_pages(colidx, c_bytes);
+        g.tripped = 0;
+        g.used = 1;
+        for (int j = 0; j < 3; ++j)
+            if (g.r[j].lo && mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ) != 0)
+                g.r[j].lo = g.r[j].hi = nullptr;          /* not protectable (e.g. a read-only mapping) */
+        return k;
+    }
+    return -1;
+}
+
+static void guard_disarm(int slot)
+{
+    if (slot < 0) return;
+    GuardSlot &g = g_guards[slot];
+    for (int j = 0; j < 3; ++j)
+        if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ | PROT_WRITE);
+    g.used = 0;
+}
+
+/* ------------------------------------------------------------------------
+ * copy threads: pageable caller vectors go through pinned bounce buffers, and one
+ * core copies 1.2 MB (NPB class C) in ~75 us -- as long as the product itself.
+ * A few helper threads (B200_SPMV_COPY_THREADS, default 4 including the caller)
+ * split copies of >= 256 KB.  They sleep on a condition variable between calls.
+ * ---------------------------------------------------------------------- */
+struct CopyPool {
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    int nworkers;
+    uint64_t generation;
+    char *dst; const char *src; size_t bytes; int nsplit;
+    std::atomic<int> pending;
+    bool started;
+};
+static CopyPool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, nullptr, nullptr, 0, 0, {0}, false};
+
+static void copy_share(char *dst, const char *src, size_t bytes, int nsplit, int k)
+{
+    const size_t unit = 4096;
+    const size_t per = ((bytes + (size_t)nsplit - 1) / nsplit + unit - 1) / unit * unit;
+    const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
+    if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
+}
+
+static void *copy_worker(void *arg)
+{
+    const int id = (int)(intptr_t)arg;            /* 1 .. nworkers */
+    uint64_t seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv, &g_pool.mu);
+        seen = g_pool.generation;
+        char *dst = g_pool.dst; const char *src = g_pool.src;
+        const size_t bytes = g_pool.bytes; const int nsplit = g_pool.nsplit;
+        pthread_mutex_unlock(&g_pool.mu);
+        if (id < nsplit) copy_share(dst, src, bytes, nsplit, id);
+        g_pool.pending.fetch_sub(1, std::memory_order_release);
+        pthread_mutex_lock(&g_pool.mu);
+    }
+    return nullptr;
+}
+
+static void fast_copy(void *dst, const void *src, size_t bytes)
+{
+    if (!g_pool.started) {
+        g_pool.started = true;
+        const int want = std::max(1, std::min(16, env_int("B200_SPMV_COPY_THREADS", 4))) - 1;
+        for (int i = 0; i < want; ++i) {
+            pthread_t t;
+            if (pthread_create(&t, nullptr, copy_worker, (void *)(intptr_t)(i + 1)) != 0) break;
+            pthread_detach(t);
+            g_pool.nworkers++;
+        }
+    }
+    if (g_pool.nworkers == 0 || bytes < (256u << 10)) { memcpy(dst, src, bytes); return; }
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.dst = (char *)dst; g_pool.src = (const char *)src; g_pool.bytes = bytes;
+    g_pool.nsplit = g_pool.nworkers + 1;
+    g_pool.pending.store(g_pool.nworkers, std::memory_order_relaxed);
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.cv);
+    pthread_mutex_unlock(&g_pool.mu);
+    copy_share((char *)dst, (const char *)src, bytes, g_pool.nworkers + 1, 0);
+    while (g_pool.pending.load(std::memory_order_acquire) > 0) { }     /* tens of microseconds */
+}
+
+/* ------------------------------------------------------------------------
+ * configuration
+ * ---------------------------------------------------------------------- */
+static void dump_stats_at_exit(void)
+{
+    if (!env_int("B200_SPMV_STATS", 0)) return;
+    fprintf(stderr,
+            "libb200-spmv stats: calls=%llu uploads=%llu launches=%llu kernel_ms=%.3f "
+            "e2e_ms=%.3f upload_ms=%.3f h2d_MB=%.3f d2h_MB=%.3f devices=%d\n",
+            (unsigned long long)g_stats.calls, (unsigned long long)g_stats.uploads,
+            (unsigned long long)g_stats.kernel_launches, g_stats.kernel_ms, g_stats.e2e_ms,
+            g_stats.upload_ms, g_stats.h2d_bytes / 1e6, g_stats.d2h_bytes / 1e6, std::max(g_ndev, 1));
+}
+
+/* B200_SPMV_DEVICES = "all" | "0,1,2,3": the devices the drop-in symbols spread a
+ * large matrix over (ABI mode).  Unset: the one default device. */
+static void parse_devices_locked(void)
+{
+    g_ndev = 0;
+    int count = 0;
+    CUDA_OK(cudaGetDeviceCount(&count));
+    const char *v = getenv("B200_SPMV_DEVICES");
+    if (v && *v) {
+        if (!strcmp(v, "all")) {
+            for (int d = 0; d < count && g_ndev < kMaxDevices; ++d) g_devs[g_ndev++] = d;
+        } else {
+            const char *p = v;
+            while (*p && g_ndev < kMaxDevices) {
+                char *end = nullptr;
+                const long d = strtol(p, &end, 10);
+                if (end == p) die("B200_SPMV_DEVICES=%s: not a comma-separated device list", v);
+                if (d < 0 || d >= count) die("B200_SPMV_DEVICES=%s: device %ld does not exist (%d visible)", v, d, count);
+                for (int k = 0; k < g_ndev; ++k)
+                    if (g_devs[k] == (int)d) die("B200_SPMV_DEVICES=%s: device %ld listed twice", v, d);
+                g_devs[g_ndev++] = (int)d;
+                p = *end == ',' ? end + 1 : end;
+            }
+        }
+    }
+    if (g_ndev == 0) g_devs[g_ndev++] = default_device_locked();
+    if (g_ndev > 1) {
+        /* one process: plain peer access, no IPC handles */
+        for (int i = 0; i < g_ndev; ++i) {
+            DeviceScope scope(g_devs[i]);
+            for (int j = 0; j < g_ndev; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                CUDA_OK(cudaDeviceCanAccessPeer(&can, g_devs[i], g_devs[j]));
+                if (!can) die("B200_SPMV_DEVICES: device %d cannot access device %d", g_devs[i], g_devs[j]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(g_devs[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else CUDA_OK(e);
+            }
+        }
+    }
+}
+
+static void ensure_conf_locked(void)
+{
+    ensure_init_locked(-1);
+    if (g_conf_ready) return;
+    g_validate = env_int("B200_SPMV_VALIDATE", 1);
+    g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
+    g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
+    g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
+    g_auto_pin = env_int("B200_SPMV_PIN_HOST", 0);
+    g_guard = env_int("B200_SPMV_GUARD", 1);
+    {
+        const char *v = getenv("B200_SPMV_MULTI_MIN_NNZ");
+        if (v && *v) g_multi_min_nnz = atoll(v);
+    }
+    parse_devices_locked();
+    memset(&g_stats, 0, sizeof g_stats);
+    atexit(dump_stats_at_exit);
+    g_conf_ready = true;
+}
+
+/* ------------------------------------------------------------------------
+ * staleness checks
+ * ---------------------------------------------------------------------- */
+static inline uint64_t mix(uint64_t h, uint64_t v)
+{
+    h = (h ^ v) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+static uint64_t hash_bytes(const void *p, size_t bytes, uint64_t h)
+{
+    const unsigned char *c = (const unsigned char *)p;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t v;
+        memcpy(&v, c + i, 8);
+        h = mix(h, v);
+    }
+    uint64_t tail = 0;
+    if (i < bytes) memcpy(&tail, c + i, bytes - i);
+    return mix(h, tail ^ (uint64_t)bytes);
+}
+
+/* checked on every call: all of rowstr / a / colidx when they are small (<= 64 KB in
+ * total: the guard cannot protect arrays below a page), else 64 evenly spaced probes
+ * of each array */
+static uint64_t fingerprint(const void *a, const int *rowstr, const int *colidx,
+                            int rows, int64_t nnz, size_t es)
+{
+    uint64_t h = 1469598103934665603ull;
+    if (rows <= 0) return h;
+    const int64_t base = (int64_t)rowstr[0] - 1;
+    const size_t total = (size_t)nnz * (es + 4) + ((size_t)rows + 1) * 4;
+    if (total <= (64u << 10)) {
+        h = hash_bytes(rowstr, ((size_t)rows + 1) * 4, h);
+        h = hash_bytes((const char *)a + (size_t)base * es, (size_t)nnz * es, h);
+        return hash_bytes(colidx + base, (size_t)nnz * 4, h);
+    }
+    const int probes = 64;
+    for (int k = 0; k < probes && nnz > 0; ++k) {
+        const int64_t i = base + (nnz - 1) * k / (probes - 1);
+        uint64_t v = 0;
+        memcpy(&v, (const char *)a + (size_t)i * es, es);
+        h = mix(h, v);
+        h = mix(h, (uint64_t)(uint32_t)colidx[i]);
+    }
+    for (int k = 0; k < probes; ++k) {
+        const int64_t i = (int64_t)rows * k / (probes - 1);
+        h = mix(h, (uint64_t)(uint32_t)rowstr[i]);
+    }
+    return h;
+}
+
+/* rolling check: a / colidx are cut into 32 KB windows hashed at upload; every call
+ * re-hashes one window (~2 us), so an in-place change the probes miss is found within
+ * one sweep over the windows even when the guard is off */
+static const size_t kWindow = 32u << 10;
+
+static size_t window_count(int64_t nnz, size_t es)
+{
+    return ((size_t)nnz * es + kWindow - 1) / kWindow + ((size_t)nnz * 4 + kWindow - 1) / kWindow;
+}
+
+static uint64_t window_hash(const CacheEntry &e, size_t w)
+{
+    const size_t es = elem_size(e.dtype);
+    const int64_t base = e.rows > 0 ? (int64_t)e.rowstr[0] - 1 : 0;
+    const size_t wa = ((size_t)e.nnz * es + kWindow - 1) / kWindow;
+    const char *p; size_t total;
+    if (w < wa) { p = (const char *)e.a + (size_t)base * es; total = (size_t)e.nnz * es; }
+    else { p = (const char *)(e.colidx + base); total = (size_t)e.nnz * 4; w -= wa; }
+    const size_t lo = w * kWindow, hi = std::min(total, lo + kWindow);
+    return hash_bytes(p + lo, hi - lo, 0x243F6A8885A308D3ull);
+}
+
+/* ------------------------------------------------------------------------
+ * pinned caller vectors
+ * ---------------------------------------------------------------------- */
+/* Device-usable alias of a pinned (cudaHostAlloc'ed or registered) host range, or NULL
+ * when any part of [p, p + bytes) is pageable: first and last byte must both be pinned
+ * and map to device addresses `bytes - 1` apart (one mapping, or adjacent ones). */
+static void *pinned_device_alias(const void *p, size_t bytes)
+{
+    if (bytes == 0) return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a0.type != cudaMemoryTypeHost || !a0.devicePointer) return nullptr;
+    if (cudaPointerGetAttributes(&a1, (const char *)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a1.type != cudaMemoryTypeHost || !a1.devicePointer) return nullptr;
+    if ((char *)a1.devicePointer - (char *)a0.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;
+    return a0.devicePointer;
+}
+
+static int register_range_locked(void *p, size_t bytes)
+{
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    PinnedRange r = {(char *)p, (char *)p + bytes};
+    g_pinned.push_back(r);
+    return 0;
+}
+
+/* B200_SPMV_PIN_HOST=1: register a caller vector the first time it is seen, so later calls
+ * move it in place instead of through the bounce buffer.  Only safe for vectors that
+ * outlive the library use (NPB's COMMON arrays, pagerank's two std::vectors): a range
+ * that is freed and mapped again while registered would be read through a stale
+ * mapping.  Off by default for that reason. */
+static void maybe_auto_pin(const void *p, size_t bytes)
+{
+    if (!g_auto_pin || bytes == 0) return;
+    const char *c = (const char *)p;
+    for (const PinnedRange &r : g_pinned)
+        if (c >= r.lo && c + bytes <= r.hi) return;
+    register_range_locked((void *)p, bytes);
+}
+
+/* ------------------------------------------------------------------------
+ * cache
+ * ---------------------------------------------------------------------- */
+static void release_entry_locked(CacheEntry &e)
+{
+    guard_disarm(e.guard_slot);
+    for (int p = 0; p < e.nparts; ++p) {
+        Part &pt = e.part[p];
+        DeviceScope scope(pt.ctx->device);
+        cudaStreamSynchronize(pt.ctx->stream);
+        release_locked(pt.m);
+        cudaFree(pt.d_x);
+        cudaFree(pt.d_y);
+    }
+    if (e.h_x) cudaFreeHost(e.h_x);
+    if (e.h_y) cudaFreeHost(e.h_y);
+}
+
+static void build_entry_locked(CacheEntry &e)
+{
+    const size_t es = elem_size(e.dtype);
+    const bool multi = g_ndev > 1 && e.nnz >= g_multi_min_nnz && e.rows >= g_ndev;
+    e.nparts = multi ? g_ndev : 1;
+    int bounds[kMaxDevices + 1];
+    if (multi) b200_spmv_partition_rows(e.rowstr, e.rows, e.nparts, bounds);
+    else { bounds[0] = 0; bounds[1] = e.rows; }
+    e.ncols = 0;
+    for (int p = 0; p < e.nparts; ++p) {
+        Part &pt = e.part[p];
+        pt.ctx = ctx_for_device_locked(multi ? g_devs[p] : g_devs[0]);
+        pt.row_lo = bounds[p]; pt.row_hi = bounds[p + 1];
+        pt.m = nullptr; pt.d_x = pt.d_y = nullptr;
+        if (pt.row_hi > pt.row_lo || !multi) {
+            /* a row block is addressed exactly as the ABI would: (a, rowstr + lo, colidx, hi - lo) */
+            pt.m = upload_locked(pt.ctx, e.a, e.rowstr + pt.row_lo, e.colidx, pt.row_hi - pt.row_lo,
+                                 e.dtype, B200_KERNEL_AUTO);
+            e.ncols = std::max(e.ncols, pt.m->ncols);
+        }
+    }
+    e.x_bytes = (size_t)std::max(e.ncols, 1) * es;
+    e.y_bytes = (size_t)std::max(e.rows, 1) * es;
+    const size_t x_used = (size_t)e.ncols * es;
+    for (int p = 0; p < e.nparts; ++p) {
+        Part &pt = e.part[p];
+        DeviceScope scope(pt.ctx->device);
+        /* slice of x this device fetches: 16-byte granules */
+        pt.x_lo = p == 0 ? 0 : (x_used * (size_t)p / e.nparts) / 16 * 16;
+        pt.x_hi = p == e.nparts - 1 ? x_used : (x_used * (size_t)(p + 1) / e.nparts) / 16 * 16;
+        CUDA_OK(cudaMalloc((void **)&pt.d_x, std::max<size_t>(e.x_bytes, 16)));
+        CUDA_OK(cudaMalloc((void **)&pt.d_y, std::max<size_t>((size_t)(pt.row_hi - pt.row_lo) * es, 16)));
+    }
+    CUDA_OK(cudaHostAlloc(&e.h_x, e.x_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    CUDA_OK(cudaHostAlloc(&e.h_y, e.y_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    if (g_verbose && multi) {
+        fprintf(stderr, "libb200-spmv: matrix rows=%d nnz=%lld spread over %d devices:", e.rows,
+                (long long)e.nnz, e.nparts);
+        for (int p = 0; p < e.nparts; ++p)
+            fprintf(stderr, " dev%d[rows %d..%d, %s]", e.part[p].ctx->device, e.part[p].row_lo, e.part[p].row_hi,
+                    e.part[p].m ? b200_spmv_kernel_name(e.part[p].m) : "empty");
+        fprintf(stderr, "\n");
+    }
+}
+
+static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *colidx,
+                                 int rows, int dtype)
+{
+    const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - rowstr[0] : 0;
+    const size_t es = elem_size(dtype);
+    ++g_tick;
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+        CacheEntry &e = g_cache[i];
+        if (e.a == a && e.rowstr == rowstr && e.colidx == colidx && e.rows == rows &&
+            e.nnz == nnz && e.dtype == dtype) {
+            bool stale = e.guard_slot >= 0 && g_guards[e.guard_slot].tripped;
+            if (!stale && g_validate) {
+                stale = fingerprint(a, rowstr, colidx, rows, nnz, es) != e.fingerprint;
+                if (!stale && !e.win_hash.empty()) {
+                    stale = window_hash(e, e.win_next) != e.win_hash[e.win_next];
+                    e.win_next = (e.win_next + 1) % e.win_hash.size();
+                }
+            }
+            if (stale) {
+                if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
+                release_entry_locked(e);
+                g_cache[i] = g_cache.back();
+                g_cache.pop_back();
+                break;
+            }
+            e.last_use = g_tick;
+            return &e;
+        }
+    }
+    /* miss: upload (evict the least recently used entry beyond the cap) */
+    const double t0 = now_ms();
+    if ((int)g_cache.size() >= g_cache_cap) {
+        size_t victim = 0;
+        for (size_t i = 1; i < g_cache.size(); ++i)
+            if (g_cache[i].last_use < g_cache[victim].last_use) victim = i;
+        release_entry_locked(g_cache[victim]);
+        g_cache[victim] = g_cache.back();
+        g_cache.pop_back();
+    }
+    g_cache.emplace_back();
+    CacheEntry &e = g_cache.back();
+    e.a = a; e.rowstr = rowstr; e.colidx = colidx; e.rows = rows; e.nnz = nnz; e.dtype = dtype;
+    e.last_use = g_tick;
+    e.guard_slot = -1;
+    e.win_next = 0;
+    e.h_x = e.h_y = nullptr;
+    build_entry_locked(e);
+    if (g_validate) {
+        e.fingerprint = fingerprint(a, rowstr, colidx, rows, nnz, es);
+        const size_t total = (size_t)nnz * (es + 4) + ((size_t)rows + 1) * 4;
+        if (total > (64u << 10)) {
+            e.win_hash.resize(window_count(nnz, es));
+            for (size_t w = 0; w < e.win_hash.size(); ++w) e.win_hash[w] = window_hash(e, w);
+        }
+    } else {
+        e.fingerprint = 0;
+    }
+    const size_t last = rows > 0 ? (size_t)rowstr[rows] - 1 : 0;          /* entries up to the last offset */
+    e.guard_slot = guard_arm(a, last * es, rowstr, ((size_t)rows + 1) * sizeof(int), colidx, last * sizeof(int));
+    g_stats.uploads++;
+    g_stats.upload_ms += now_ms() - t0;
+    return &e;
+}
+
+/* ------------------------------------------------------------------------
+ * one call
+ * ---------------------------------------------------------------------- */
+static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
+                           const int *colidx, const int *rows, int dtype)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_conf_locked();
+    const int n = *rows;
+    CacheEntry *ep = lookup_locked(a, rowstr, colidx, n, dtype);
+    CacheEntry &e = *ep;
+    const double t0 = now_ms();
+    if (n > 0) {
+        const size_t es = elem_size(dtype);
+        const size_t x_used = (size_t)e.ncols * es;
+        maybe_auto_pin(iv, e.x_bytes);
+        maybe_auto_pin(ov, e.y_bytes);
+        /* x: host -> device (gpu.c:264).  Pinned caller memory is read in place over PCIe
+         * by a copy kernel on the library's stream (no copy-engine hop); pageable memory
+         * goes through the pinned bounce buffer first. */
+        const char *x_pinned = nullptr;       /* host pointer to pinned x, for the copy engine */
+        const char *x_alias = nullptr;        /* its device alias, for the copy kernel */
+        if (x_used > 0) {
+            x_alias = (const char *)pinned_device_alias(iv, x_used);
+            x_pinned = (const char *)iv;
+            if (!x_alias) {
+                fast_copy(e.h_x, iv, x_used);
+                x_pinned = (const char *)e.h_x;
+                x_alias = (const char *)pinned_device_alias(e.h_x, x_used);
+                if (!x_alias) die("the pinned bounce buffer has no device alias");
+            }
+        }
+        /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
+         * straight into pinned host memory (the caller's, else the bounce buffer). */
+        char *y_alias = (char *)pinned_device_alias(ov, (size_t)n * es);
+        const bool y_direct = y_alias != nullptr;
+        char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
+        if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
+
+        const bool multi = e.nparts > 1;
+        for (int p = 0; p < e.nparts; ++p) {
+            Part &pt = e.part[p];
+            DeviceScope scope(pt.ctx->device);
+            cudaStream_t s = pt.ctx->stream;
+            if (pt.x_hi > pt.x_lo) {
+                const size_t bytes = pt.x_hi - pt.x_lo;
+                if (g_zero_copy || multi) {
+                    /* one kernel: read the slice over this device's PCIe link, store it into
+                     * every device's x buffer (the peers' over NVLink) */
+                    void *dst[kMaxDevices];
+                    for (int j = 0; j < e.nparts; ++j) dst[j] = e.part[j].d_x + pt.x_lo;
+                    launch_copy_in_multi(x_alias + pt.x_lo, dst, e.nparts, bytes, s);
+                } else {
+                    CUDA_OK(cudaMemcpyAsync(pt.d_x + pt.x_lo, x_pinned + pt.x_lo, bytes, cudaMemcpyHostToDevice, s));
+                }
+            }
+            if (multi) CUDA_OK(cudaEventRecord(pt.ctx->ev_x, s));
+        }
+        int launched = 0;
+        for (int p = 0; p < e.nparts; ++p) {
+            Part &pt = e.part[p];
+            DeviceScope scope(pt.ctx->device);
+            cudaStream_t s = pt.ctx->stream;
+            if (multi)
+                for (int j = 0; j < e.nparts; ++j)
+                    if (j != p) CUDA_OK(cudaStreamWaitEvent(s, e.part[j].ctx->ev_x, 0));
+            const int prow = pt.row_hi - pt.row_lo;
+            if (!pt.m || prow <= 0) continue;
+            if (g_time_kernels) CUDA_OK(cudaEventRecord(pt.ctx->ev0, s));
+            char *y_target = nullptr;
+            if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
+                y_target = y_alias + (size_t)pt.row_lo * es;
+            launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, nullptr);
+            if (g_time_kernels) CUDA_OK(cudaEventRecord(pt.ctx->ev1, s));
+            if (!y_target)
+                CUDA_OK(cudaMemcpyAsync(y_host + (size_t)pt.row_lo * es, pt.d_y, (size_t)prow * es,
+                                        cudaMemcpyDeviceToHost, s));
+        }
+        float kernel_ms = 0.f;
+        for (int p = 0; p < e.nparts; ++p) {
+            Part &pt = e.part[p];
+            DeviceScope scope(pt.ctx->device);
+            CUDA_OK(cudaStreamSynchronize(pt.ctx->stream));
+            if (g_time_kernels && pt.m && pt.row_hi > pt.row_lo) {
+                float ms = 0.f;
+                CUDA_OK(cudaEventElapsedTime(&ms, pt.ctx->ev0, pt.ctx->ev1));
+                kernel_ms = std::max(kernel_ms, ms);
+            }
+        }
+        if (!y_direct) fast_copy(ov, e.h_y, (size_t)n * es);
+        g_stats.kernel_ms += kernel_ms;
+        g_stats.kernel_launches += (uint64_t)launched;
+        g_stats.h2d_bytes += x_used;
+        g_stats.d2h_bytes += (size_t)n * es;
+    }
+    g_stats.calls++;
+    g_stats.e2e_ms += now_ms() - t0;
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void *spmv_harness_(double *ov, double *a, double *iv, int *rowstr, int *colidx, int *rows)
+{
+    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F64);
+    return NULL;
+}
+
+extern "C" void *f_spmv_harness_(float *ov, float *a, float *iv, int *rowstr, int *colidx, int *rows)
+{
+    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F32);
+    return NULL;
+}
+
+extern "C" void b200_spmv_invalidate(void)
+{
+    pthread_mutex_lock(&g_lock);
+    for (CacheEntry &e : g_cache) release_entry_locked(e);
+    g_cache.clear();
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" int b200_spmv_devices_in_use(void)
+{
+    pthread_mutex_lock(&g_lock);
+    int n = 0;
+    for (const CacheEntry &e : g_cache) n = std::max(n, e.nparts);
+    pthread_mutex_unlock(&g_lock);
+    return n;
+}
+
+extern "C" void b200_spmv_get_stats(b200_spmv_stats *out)
+{
+    pthread_mutex_lock(&g_lock);
+    *out = g_stats;
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void b200_spmv_reset_stats(void)
+{
+    pthread_mutex_lock(&g_lock);
+    memset(&g_stats, 0, sizeof g_stats);
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" int b200_spmv_pin_host(void *ptr, size_t bytes)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_conf_locked();
+    const int rc = register_range_locked(ptr, bytes);
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+extern "C" int b200_spmv_unpin_host(void *ptr)
+{
+    int rc = -1;
+    pthread_mutex_lock(&g_lock);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+        if (g_pinned[i].lo == (char *)ptr) {
+            cudaHostUnregister(ptr);
+            g_pinned[i] = g_pinned.back();
+            g_pinned.pop_back();
+            rc = 0;
+            break;
+        }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}

@@ -1,43 +1,32 @@
 /*
- * b200_host.cu -- host layer of libb200-spmv.so: the libspmv ABI on top of a
- * device-resident matrix cache.  Thin C-style code over the CUDA runtime only
- * (no cuSPARSE, no cuBLAS, no CPU fallback).
+ * b200_host.cu -- host layer of libb200-spmv.so, part 1: per-device contexts,
+ * upload (layout selection and build) and launch of a resident CSR row block,
+ * i.e. the resident-matrix API of include/b200_spmv.h part 2.  Thin C-style
+ * code over the CUDA runtime only (no cuSPARSE, no cuBLAS, no CPU fallback).
+ * The libspmv ABI itself (cache, write guard, x / y movement, several devices)
+ * lives in b200_dropin.cu.
  *
  * Reference behaviour mirrored (and where it deliberately differs):
  *   libspmv/gpu.c:36-85    setup(): lazy one-time init, device buffers sized
  *                          from (rows, cols, nnz).  Here buffers belong to a
- *                          cache entry and are freed on eviction (gpu.c leaks
+ *                          resident matrix and are freed with it (gpu.c leaks
  *                          the old ones on every shape change).
  *   libspmv/gpu.c:213-223  column count = max(colidx); gpu.c scans the host
  *                          array with an off-by-one loop, here a device
  *                          reduction over the uploaded colidx does it.
- *   libspmv/gpu.c:227-262  matrix kept resident, keyed by the host pointers;
- *                          here the key also carries rows and nnz, and several
- *                          matrices can be resident at once.
- *   libspmv/gpu.c:140-209  mprotect/SIGSEGV invalidation: not installed (no
- *                          in-scope caller mutates its matrix); replaced by
- *                          b200_spmv_invalidate() and a sampled fingerprint
- *                          check of the host arrays on every call (on by
- *                          default, B200_SPMV_VALIDATE=0 switches it off).
- *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but through
- *                          pinned staging (or direct DMA when the caller's
- *                          vector is already pinned) on the library's stream.
  *   libspmv/gpu.c:42-80    errors: assert -> here message on stderr + abort().
+ *
+ * State is per device (DevCtx): a process may hold resident matrices on several
+ * GPUs; every entry point makes the device of the object it works on current
+ * and restores the caller's device before it returns.
  */
-#include "../../include/b200_spmv.h"
-#include "spmv_kernels.cuh"
+#include "host_internal.h"
 
-#include <cuda_runtime.h>
-
-#include <pthread.h>
-#include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/mman.h>
 #include <time.h>
-#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -45,10 +34,11 @@
 
 using namespace b200;
 
-#define B200_VERSION "b200-spmv 0.1 (sm_100a)"
+#define B200_VERSION "b200-spmv 0.2 (sm_100a)"
 
-/* ------------------------------------------------------------------------ */
-static void die(const char *fmt, ...)
+namespace b200 {
+
+void die(const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -59,215 +49,75 @@ static void die(const char *fmt, ...)
     abort();
 }
 
-#define CUDA_OK(call)                                                          \
-    do {                                                                       \
-        cudaError_t e_ = (call);                                               \
-        if (e_ != cudaSuccess)                                                 \
-            die("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
-                cudaGetErrorString(e_));                                       \
-    } while (0)
-
-static double now_ms(void)
+double now_ms(void)
 {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-static int env_int(const char *name, int dflt)
+int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
 
-/* ------------------------------------------------------------------------
- * resident matrix
- * ---------------------------------------------------------------------- */
-struct b200_matrix {
-    int dtype;                 /* B200_F64 / B200_F32 */
-    int kernel;                /* family in use */
-    int lanes;                 /* VECTOR: lanes per row */
-    int device;
-    int rows, ncols;
-    int64_t nnz;
-    DevCsr dev;                /* device pointers */
-    void *d_val; int *d_col; int *d_rowptr; int *d_rowblk;
-    int64_t resident_bytes;
-    UploadScan scan;
-    /* PANEL layout (when kernel == B200_KERNEL_PANEL) */
-    DevPanel panel;
-    void *d_pval; uint16_t *d_pcol; ushort4 *d_meta; int *d_slice_off;
-    /* SELL layout (when kernel == B200_KERNEL_SELL) */
-    DevSell sell;
-    int *d_scol; int4 *d_chunks; int2 *d_multi; int *d_multi_rows; void *d_carry;
-    /* staging owned by the drop-in path (allocated lazily) */
-    void *d_x, *d_y;           /* device vectors */
-    void *h_x, *h_y;           /* pinned bounce buffers */
-    size_t x_bytes, y_bytes;
-};
+pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+int g_verbose = 0;
 
-static size_t elem_size(int dtype) { return dtype == B200_F32 ? 4 : 8; }
-
-/* global state ----------------------------------------------------------- */
-struct CacheEntry {
-    const void *a; const int *rowstr; const int *colidx;
-    int rows; int64_t nnz; int dtype;
-    uint64_t fingerprint;
-    uint64_t last_use;
-    b200_matrix *m;
-    int guard_slot;            /* index into g_guards, -1 when unguarded */
-};
-
-struct PinnedRange { char *lo, *hi; bool ours; };
-
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static bool g_ready = false;
-static int g_device = -1;
-static int g_sm_count = 148;
-static cudaStream_t g_stream = nullptr;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static std::vector<CacheEntry> g_cache;
-static std::vector<PinnedRange> g_pinned;
-static uint64_t g_tick = 0;
-static b200_spmv_stats g_stats;
-static int g_validate = 0, g_verbose = 0, g_cache_cap = 4, g_time_kernels = 1;
-static int g_zero_copy = 1, g_auto_pin = 0;
+static int g_default_device = -1;
+static int g_device_count = 0;
+static DevCtx *g_ctx[kMaxDevices * 8];      /* indexed by device ordinal */
+
+void ensure_init_locked(int device)
+{
+    if (!g_ready) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            die("no CUDA device available (%s); this platform has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        g_device_count = std::min(count, (int)(sizeof g_ctx / sizeof g_ctx[0]));
+        g_verbose = env_int("B200_SPMV_VERBOSE", 0);
+        g_ready = true;
+    }
+    /* the device of the drop-in path: an explicit b200_spmv_init(d) wins, then
+     * B200_SPMV_DEVICE, then whatever device is current at the first call */
+    if (device >= 0) {
+        if (device >= g_device_count) die("device %d does not exist (%d visible)", device, g_device_count);
+        g_default_device = device;
+    } else if (g_default_device < 0) {
+        int d = env_int("B200_SPMV_DEVICE", -1);
+        if (d < 0) CUDA_OK(cudaGetDevice(&d));
+        if (d >= g_device_count) die("device %d does not exist (%d visible)", d, g_device_count);
+        g_default_device = d;
+    }
+}
+
+int default_device_locked(void) { return g_default_device; }
+
+DevCtx *ctx_for_device_locked(int device)
+{
+    if (device < 0 || device >= g_device_count) die("device %d out of range", device);
+    if (g_ctx[device]) return g_ctx[device];
+    DeviceScope scope(device);
+    DevCtx *c = (DevCtx *)calloc(1, sizeof *c);
+    c->device = device;
+    CUDA_OK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&c->ev0));
+    CUDA_OK(cudaEventCreate(&c->ev1));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+    g_ctx[device] = c;
+    return c;
+}
+
+}  // namespace b200
 
 /* ------------------------------------------------------------------------
- * Opt-in write guard (B200_SPMV_GUARD=1): the reference's cache-coherence
- * device (libspmv/gpu.c:140-209, ALIGN macro :204-209): the host pages of a
- * resident matrix are made read-only and a SIGSEGV handler invalidates the
- * cache entry when the caller writes to them, chaining to any handler that was
- * installed before (gpu.c:180-181).  Differences: only pages lying entirely
- * inside an array are protected (gpu.c rounds outwards, so a write to a
- * neighbouring variable on a shared page silently drops the protection -- in
- * NPB `x` follows `a` in COMMON), and several matrices can be guarded.
- * The handler only touches this fixed table (async-signal-safe).
+ * upload
  * ---------------------------------------------------------------------- */
-struct GuardRange { char *lo, *hi; };
-struct GuardSlot {
-    volatile int used;         /* 1 while a cache entry owns the slot */
-    volatile int tripped;      /* set by the handler: host copy was written */
-    GuardRange r[3];
-};
-static const int kMaxGuards = 16;
-static GuardSlot g_guards[kMaxGuards];
-static struct sigaction g_old_segv;
-static bool g_guard_installed = false;
-static int g_guard = 0;
-
-static void guard_handler(int sig, siginfo_t *si, void *ctx)
-{
-    char *addr = (char *)si->si_addr;
-    for (int k = 0; k < kMaxGuards; ++k) {
-        GuardSlot &g = g_guards[k];
-        if (!g.used) continue;
-        for (int j = 0; j < 3; ++j) {
-            if (g.r[j].lo && addr >= g.r[j].lo && addr < g.r[j].hi) {
-                for (int q = 0; q < 3; ++q)
-                    if (g.r[q].lo && g.r[q].hi > g.r[q].lo)
-                        mprotect(g.r[q].lo, (size_t)(g.r[q].hi - g.r[q].lo), PROT_READ | PROT_WRITE);
-                g.tripped = 1;
-                return;                           /* the faulting store is retried */
-            }
-        }
-    }
-    /* not ours: chain (gpu.c:180-181) or fall back to the default action */
-    if ((g_old_segv.sa_flags & SA_SIGINFO) && g_old_segv.sa_sigaction) {
-        g_old_segv.sa_sigaction(sig, si, ctx);
-    } else if (g_old_segv.sa_handler != SIG_DFL && g_old_segv.sa_handler != SIG_IGN &&
-               g_old_segv.sa_handler) {
-        g_old_segv.sa_handler(sig);
-    } else {
-        signal(SIGSEGV, SIG_DFL);
-    }
-}
-
-static GuardRange inner_pages(const void *p, size_t bytes)
-{
-    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGE_SIZE);
-    uintptr_t lo = ((uintptr_t)p + page - 1) / page * page;
-    uintptr_t hi = ((uintptr_t)p + bytes) / page * page;
-    GuardRange r = {nullptr, nullptr};
-    if (hi > lo) { r.lo = (char *)lo; r.hi = (char *)hi; }
-    return r;
-}
-
-static int guard_arm(const void *a, size_t a_bytes, const int *rowstr, size_t r_bytes,
-                     const int *colidx, size_t c_bytes)
-{
-    if (!g_guard) return -1;
-    if (!g_guard_installed) {
-        struct sigaction sa;
-        memset(&sa, 0, sizeof sa);
-        sa.sa_flags = SA_SIGINFO;
-        sigemptyset(&sa.sa_mask);
-        sa.sa_sigaction = guard_handler;
-        if (sigaction(SIGSEGV, &sa, &g_old_segv) != 0) return -1;
-        g_guard_installed = true;
-    }
-    for (int k = 0; k < kMaxGuards; ++k) {
-        GuardSlot &g = g_guards[k];
-        if (g.used) continue;
-        g.r[0] = inner_pages(a, a_bytes);
-        g.r[1] = inner_pages(rowstr, r_bytes);
-        g.r[2] = inner_pages(colidx, c_bytes);
-        g.tripped = 0;
-        g.used = 1;
-        for (int j = 0; j < 3; ++j)
-            if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ);
-        return k;
-    }
-    return -1;
-}
-
-static void guard_disarm(int slot)
-{
-    if (slot < 0) return;
-    GuardSlot &g = g_guards[slot];
-    for (int j = 0; j < 3; ++j)
-        if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ | PROT_WRITE);
-    g.used = 0;
-}
-
-static void dump_stats_at_exit(void)
-{
-    if (!env_int("B200_SPMV_STATS", 0)) return;
-    fprintf(stderr,
-            "libb200-spmv stats: calls=%llu uploads=%llu launches=%llu kernel_ms=%.3f "
-            "e2e_ms=%.3f upload_ms=%.3f h2d_MB=%.3f d2h_MB=%.3f\n",
-            (unsigned long long)g_stats.calls, (unsigned long long)g_stats.uploads,
-            (unsigned long long)g_stats.kernel_launches, g_stats.kernel_ms, g_stats.e2e_ms,
-            g_stats.upload_ms, g_stats.h2d_bytes / 1e6, g_stats.d2h_bytes / 1e6);
-}
-
-static void ensure_init_locked(int device)
-{
-    if (g_ready) return;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        die("no CUDA device available (%s); this platform has no CPU fallback",
-            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0) device = env_int("B200_SPMV_DEVICE", -1);
-    if (device >= 0) CUDA_OK(cudaSetDevice(device));
-    CUDA_OK(cudaGetDevice(&g_device));
-    CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, g_device));
-    CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaEventCreate(&g_ev0));
-    CUDA_OK(cudaEventCreate(&g_ev1));
-    g_validate = env_int("B200_SPMV_VALIDATE", 1);
-    g_verbose = env_int("B200_SPMV_VERBOSE", 0);
-    g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
-    g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
-    g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
-    g_auto_pin = env_int("B200_SPMV_PIN_HOST", 0);
-    g_guard = env_int("B200_SPMV_GUARD", 0);
-    memset(&g_stats, 0, sizeof g_stats);
-    atexit(dump_stats_at_exit);
-    g_ready = true;
-}
-
 /* ------------------------------------------------------------------------
  * upload
  * ---------------------------------------------------------------------- */
@@ -335,8 +185,8 @@ static bool panel_plan_ring(const b200_matrix *m, PanelPlan *pl)
     const int kTmax = std::max(64, std::min(768, env_int("B200_SPMV_PANEL_TMAX", 512)));
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) {
-        const int passes = (int)((m->rows + (long long)g_sm_count * kRmax - 1) / ((long long)g_sm_count * kRmax));
-        R = (int)((m->rows + (long long)g_sm_count * passes - 1) / ((long long)g_sm_count * passes));
+        const int passes = (int)((m->rows + (long long)m->ctx->sm_count * kRmax - 1) / ((long long)m->ctx->sm_count * kRmax));
+        R = (int)((m->rows + (long long)m->ctx->sm_count * passes - 1) / ((long long)m->ctx->sm_count * passes));
     }
     R = std::max(64, std::min(kRmax, R));
     int G = env_int("B200_SPMV_PANEL_G", 0);
@@ -396,10 +246,10 @@ static bool panel_plan_beats_sell(const b200_matrix *m, const PanelPlan &pl)
     const double es = (double)elem_size(m->dtype);
     const double nblk = (double)((m->rows + pl.R - 1) / pl.R);
     const double stream = (double)m->nnz * (es + 2) * 1.06 + (double)m->rows * pl.P * 2;
-    const double waves = std::ceil(nblk / g_sm_count);
+    const double waves = std::ceil(nblk / m->ctx->sm_count);
     const double per_panel = pl.nbuf == 1 ? 1.4e-6 : 0.65e-6;
-    const double t_panel = stream / 5.5e12 * std::max(1.0, waves * g_sm_count / nblk) + waves * pl.P * per_panel;
-    const double t_sell = (double)m->nnz * 1.29 / (g_sm_count * 1.965e9);
+    const double t_panel = stream / 5.5e12 * std::max(1.0, waves * m->ctx->sm_count / nblk) + waves * pl.P * per_panel;
+    const double t_sell = (double)m->nnz * 1.29 / (m->ctx->sm_count * 1.965e9);
     return t_panel < 0.92 * t_sell;
 }
 
@@ -412,7 +262,7 @@ static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *
     int G = env_int("B200_SPMV_PANEL_G", 2);
     G = G == 1 ? 1 : 2;
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
-    if (R <= 0) R = (m->rows + g_sm_count - 1) / g_sm_count;
+    if (R <= 0) R = (m->rows + m->ctx->sm_count - 1) / m->ctx->sm_count;
     const int gran = 32 * G;
     R = std::max(gran, std::min(512 * G, (R + gran - 1) / gran * gran));   /* CTA <= 512 threads */
     const int spb = R / G / 32;
@@ -486,24 +336,24 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     int *d_overflow = nullptr, *d_cnt = nullptr;
     uint16_t *d_seglen = nullptr;
     CUDA_OK(cudaMalloc((void **)&d_seglen, nseg * sizeof(uint16_t)));
-    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
+    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), m->ctx->stream));
     CUDA_OK(cudaMalloc((void **)&d_overflow, sizeof(int)));
-    CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), g_stream));
-    launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, g_stream);
+    CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), m->ctx->stream));
+    launch_panel_count(m->d_rowptr, m->d_col, m->rows, P, W, R, d_seglen, d_overflow, m->ctx->stream);
     /* fmt 0: one ushort4 per lane and tile; fmt 2: G row ids per lane and tile */
     const size_t meta_bytes = fmt == 2 ? (size_t)ntiles * R * sizeof(uint16_t) : (size_t)ntiles * Tn * sizeof(ushort4);
     CUDA_OK(cudaMalloc((void **)&m->d_meta, meta_bytes));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
     if (fmt == 2)
-        launch_panelg_sort(d_seglen, ntiles, R, G, reinterpret_cast<uint16_t *>(m->d_meta), d_cnt, g_stream);
+        launch_panelg_sort(d_seglen, ntiles, R, G, reinterpret_cast<uint16_t *>(m->d_meta), d_cnt, m->ctx->stream);
     else
-        launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, g_stream);
+        launch_panel_sort(d_seglen, ntiles, R, G, 0, m->d_meta, d_cnt, m->ctx->stream);
     CUDA_OK(cudaGetLastError());
     int overflow = 0;
     std::vector<int> cnt((size_t)nslices + 1);
-    CUDA_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     CUDA_OK(cudaFree(d_overflow));
     /* exclusive scan of the padded slice sizes (host; a few 10^4 entries) */
     long long run = 0;
@@ -530,18 +380,18 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     cnt[nslices] = (int)run;
     m->d_slice_off = d_cnt;
     CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
-                            cudaMemcpyHostToDevice, g_stream));
+                            cudaMemcpyHostToDevice, m->ctx->stream));
     const size_t nval = (size_t)run + 64;
     if (fmt == 2) {
         /* one stream: per pair row 32 value pairs followed by 32 column pairs */
         CUDA_OK(cudaMalloc(&m->d_pval, nval * (es + 2)));
-        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * (es + 2), 0, 64 * (es + 2), g_stream));
+        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * (es + 2), 0, 64 * (es + 2), m->ctx->stream));
         m->d_pcol = nullptr;
     } else {
         CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
         CUDA_OK(cudaMalloc((void **)&m->d_pcol, nval * sizeof(uint16_t)));
-        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, g_stream));
-        CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), g_stream));
+        CUDA_OK(cudaMemsetAsync((char *)m->d_pval + (size_t)run * es, 0, 64 * es, m->ctx->stream));
+        CUDA_OK(cudaMemsetAsync(m->d_pcol + run, 0, 64 * sizeof(uint16_t), m->ctx->stream));
     }
     DevPanel &pm = m->panel;
     pm.val = m->d_pval; pm.col = m->d_pcol; pm.meta = m->d_meta; pm.slice_off = m->d_slice_off;
@@ -555,18 +405,18 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     if (fmt == 2) {
         if (m->dtype == B200_F64)
             launch_panelg_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                       d_seglen, (unsigned char *)m->d_pval, g_stream);
+                                       d_seglen, (unsigned char *)m->d_pval, m->ctx->stream);
         else
             launch_panelg_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                      d_seglen, (unsigned char *)m->d_pval, g_stream);
+                                      d_seglen, (unsigned char *)m->d_pval, m->ctx->stream);
     } else if (m->dtype == B200_F64)
         launch_panel_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                  d_seglen, (double *)m->d_pval, m->d_pcol, g_stream);
+                                  d_seglen, (double *)m->d_pval, m->d_pcol, m->ctx->stream);
     else
         launch_panel_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, pm,
-                                 d_seglen, (float *)m->d_pval, m->d_pcol, g_stream);
+                                 d_seglen, (float *)m->d_pval, m->d_pcol, m->ctx->stream);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     CUDA_OK(cudaFree(d_seglen));
     if ((fmt == 2 ? panelr_smem_bytes(pm, m->dtype == B200_F32) : panel_smem_bytes(pm, m->dtype == B200_F32)) > kSmemMax)
         die("panel shared-memory budget exceeded (W=%d R=%d)", W, R);
@@ -637,15 +487,15 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     int *d_cnt = nullptr;
     const size_t nseg = (size_t)nblk * R;
     CUDA_OK(cudaMalloc((void **)&d_seglen, nseg * sizeof(uint16_t)));
-    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), g_stream));
-    launch_sell_rowlen(m->d_rowptr, m->rows, R, cap, d_seglen, g_stream);
+    CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), m->ctx->stream));
+    launch_sell_rowlen(m->d_rowptr, m->rows, R, cap, d_seglen, m->ctx->stream);
     CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)nblk * Tn * sizeof(ushort4)));
     CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_sort(d_seglen, nblk, R, G, 1, m->d_meta, d_cnt, g_stream);
+    launch_panel_sort(d_seglen, nblk, R, G, 1, m->d_meta, d_cnt, m->ctx->stream);
     CUDA_OK(cudaGetLastError());
     std::vector<int> cnt((size_t)nslices + 1);
-    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     long long run = 0;
     for (int i = 0; i < nslices; ++i) { const int c = cnt[i]; cnt[i] = (int)run; run += c; }
     if (run > 0x7fffff00LL) {
@@ -656,7 +506,7 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     cnt[nslices] = (int)run;
     m->d_slice_off = d_cnt;
     CUDA_OK(cudaMemcpyAsync(m->d_slice_off, cnt.data(), ((size_t)nslices + 1) * sizeof(int),
-                            cudaMemcpyHostToDevice, g_stream));
+                            cudaMemcpyHostToDevice, m->ctx->stream));
     const size_t nval = (size_t)run + 64;
     CUDA_OK(cudaMalloc(&m->d_pval, nval * es));
     CUDA_OK(cudaMalloc((void **)&m->d_scol, nval * sizeof(int)));
@@ -690,12 +540,12 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     }
     if (m->dtype == B200_F64)
         launch_sell_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
-                                 d_seglen, (double *)m->d_pval, m->d_scol, g_stream);
+                                 d_seglen, (double *)m->d_pval, m->d_scol, m->ctx->stream);
     else
         launch_sell_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
-                                d_seglen, (float *)m->d_pval, m->d_scol, g_stream);
+                                d_seglen, (float *)m->d_pval, m->d_scol, m->ctx->stream);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     CUDA_OK(cudaFree(d_seglen));
     m->resident_bytes = (int64_t)(nval * (es + 4) + (size_t)nblk * Tn * 8 + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
@@ -709,21 +559,42 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     return true;
 }
 
-static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *colidx,
-                                  int rows, int dtype, int kernel)
+namespace b200 {
+
+/* `on_device`: a / rowstr / colidx are DEVICE arrays of m's device (same 1-based
+ * contents); the row pointers are read back for the host passes below. */
+static b200_matrix *upload_any_locked(DevCtx *ctx, const void *a, const int *rowstr_in,
+                                      const int *colidx, int rows, int dtype, int kernel,
+                                      bool on_device)
 {
     if (rows < 0) die("negative row count %d", rows);
     if (dtype != B200_F64 && dtype != B200_F32) die("unknown dtype %d", dtype);
+    DeviceScope scope(ctx->device);
     const size_t es = elem_size(dtype);
+    std::vector<int> rowstr_copy;
+    const int *rowstr = rowstr_in;
+    if (on_device && rows > 0) {
+        rowstr_copy.resize((size_t)rows + 1);
+        CUDA_OK(cudaMemcpy(rowstr_copy.data(), rowstr_in, ((size_t)rows + 1) * sizeof(int),
+                           cudaMemcpyDeviceToHost));
+        rowstr = rowstr_copy.data();
+    }
     const int base1 = rows > 0 ? rowstr[0] : 1;               /* 1-based offset */
+    /* native-impl.c:4-10 reads a[rowstr[i]-1 ...]: an offset below 1 would read in front of
+     * the arrays; offsets must not decrease (the row-block builders rely on it) */
+    if (base1 < 1) die("rowstr[0] = %d; row offsets are 1-based", base1);
+    for (int r = 0; r < rows; ++r)
+        if (rowstr[r + 1] < rowstr[r])
+            die("rowstr is not non-decreasing at row %d (%d > %d)", r, rowstr[r], rowstr[r + 1]);
     const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - base1 : 0;
-    if (nnz < 0) die("rowstr is not non-decreasing (nnz=%lld)", (long long)nnz);
 
     b200_matrix *m = (b200_matrix *)calloc(1, sizeof *m);
     m->dtype = dtype;
     m->rows = rows;
     m->nnz = nnz;
-    m->device = g_device;
+    m->device = ctx->device;
+    m->ctx = ctx;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 
     const size_t nval = (size_t)nnz + kPadElems;
     CUDA_OK(cudaMalloc(&m->d_val, nval * es));
@@ -732,34 +603,34 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     m->resident_bytes = (int64_t)(nval * es + nval * 4 + ((size_t)rows + 1) * 4);
 
     /* padding: value 0, column 1 (a valid 1-based index) */
-    CUDA_OK(cudaMemsetAsync((char *)m->d_val + (size_t)nnz * es, 0, kPadElems * es, g_stream));
+    CUDA_OK(cudaMemsetAsync((char *)m->d_val + (size_t)nnz * es, 0, kPadElems * es, m->ctx->stream));
     {
         int ones[kPadElems];
         for (int i = 0; i < kPadElems; ++i) ones[i] = 1;
-        CUDA_OK(cudaMemcpyAsync(m->d_col + nnz, ones, sizeof ones, cudaMemcpyHostToDevice, g_stream));
-        CUDA_OK(cudaStreamSynchronize(g_stream));
+        CUDA_OK(cudaMemcpyAsync(m->d_col + nnz, ones, sizeof ones, cudaMemcpyHostToDevice, m->ctx->stream));
+        CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     }
     if (nnz > 0) {
         CUDA_OK(cudaMemcpyAsync(m->d_val, (const char *)a + (size_t)(base1 - 1) * es,
-                                (size_t)nnz * es, cudaMemcpyHostToDevice, g_stream));
+                                (size_t)nnz * es, kind, m->ctx->stream));
         CUDA_OK(cudaMemcpyAsync(m->d_col, colidx + (base1 - 1), (size_t)nnz * sizeof(int),
-                                cudaMemcpyHostToDevice, g_stream));
+                                kind, m->ctx->stream));
     }
     if (rows > 0) {
-        CUDA_OK(cudaMemcpyAsync(m->d_rowptr, rowstr, ((size_t)rows + 1) * sizeof(int),
-                                cudaMemcpyHostToDevice, g_stream));
-        launch_rebase_rowptr(m->d_rowptr, rows + 1, base1, g_stream);
+        CUDA_OK(cudaMemcpyAsync(m->d_rowptr, rowstr_in, ((size_t)rows + 1) * sizeof(int),
+                                kind, m->ctx->stream));
+        launch_rebase_rowptr(m->d_rowptr, rows + 1, base1, m->ctx->stream);
     } else {
-        CUDA_OK(cudaMemsetAsync(m->d_rowptr, 0, sizeof(int), g_stream));
+        CUDA_OK(cudaMemsetAsync(m->d_rowptr, 0, sizeof(int), m->ctx->stream));
     }
 
     /* device-side scan: column count, histogram, sortedness */
     UploadScan *d_scan = nullptr;
     CUDA_OK(cudaMalloc((void **)&d_scan, sizeof(UploadScan)));
-    launch_upload_scan(m->d_rowptr, m->d_col, rows, (int)nnz, d_scan, g_stream);
+    launch_upload_scan(m->d_rowptr, m->d_col, rows, (int)nnz, d_scan, m->ctx->stream);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(&m->scan, d_scan, sizeof(UploadScan), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaMemcpyAsync(&m->scan, d_scan, sizeof(UploadScan), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     CUDA_OK(cudaFree(d_scan));
     if (nnz == 0) { m->scan.max_col = 0; m->scan.min_col = 1; }
     if (rows == 0) { m->scan.max_len = 0; m->scan.min_len = 0; }
@@ -800,39 +671,49 @@ static b200_matrix *upload_locked(const void *a, const int *rowstr, const int *c
     }
     if (g_verbose)
         fprintf(stderr,
-                "libb200-spmv: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
+                "libb200-spmv: dev %d: uploaded %s matrix rows=%d cols=%d nnz=%lld len[min=%d max=%d] "
                 "unsorted_rows=%d blocks=%d kernel=%s panel[fmt=%d R=%d G=%d P=%d W=%d nbuf=%d ring=%dx%d padded=%lld] sell[R=%d G=%d padded=%lld long=%d/%d]\n",
-                dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
+                m->device, dtype == B200_F32 ? "f32" : "f64", rows, m->ncols, (long long)nnz,
                 m->scan.min_len, m->scan.max_len, m->scan.rows_unsorted, nblk,
                 b200_spmv_kernel_name(m), m->panel.fmt, m->panel.R, m->panel.G, m->panel.P, m->panel.W, m->panel.nbuf, m->panel.ring_S, m->panel.ring_K, m->panel.padded,
                 m->sell.R, m->sell.G, m->sell.padded, m->sell.n_long, m->sell.n_chunks);
     return m;
 }
 
-static void release_locked(b200_matrix *m)
+b200_matrix *upload_locked(DevCtx *ctx, const void *a, const int *rowstr, const int *colidx,
+                           int rows, int dtype, int kernel)
+{
+    return upload_any_locked(ctx, a, rowstr, colidx, rows, dtype, kernel, false);
+}
+
+void release_locked(b200_matrix *m)
 {
     if (!m) return;
+    DeviceScope scope(m->device);
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_rowptr); cudaFree(m->d_rowblk);
     cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
     cudaFree(m->d_scol); cudaFree(m->d_chunks); cudaFree(m->d_multi); cudaFree(m->d_multi_rows);
     cudaFree(m->d_carry);
-    if (m->d_x) cudaFree(m->d_x);
-    if (m->d_y) cudaFree(m->d_y);
-    if (m->h_x) cudaFreeHost(m->h_x);
-    if (m->h_y) cudaFreeHost(m->h_y);
     free(m);
 }
 
-static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s)
+bool exec_waits_in_kernel(const b200_matrix *m)
+{
+    return m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 2;
+}
+
+int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf)
 {
     if (m->rows == 0) return 0;
     int launched_kernels = 1;
     if (m->kernel == B200_KERNEL_PANEL) {
         if (m->panel.fmt == 2) {
+            XFlags xf = {nullptr, 0ull, 1, 0};
+            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks; }
             if (m->dtype == B200_F64)
-                launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, s);
+                launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, xf, s);
             else
-                launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+                launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, s);
         } else if (m->dtype == B200_F64)
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else
@@ -860,6 +741,8 @@ static int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t 
     return launched_kernels;
 }
 
+}  // namespace b200
+
 /* ------------------------------------------------------------------------
  * public resident-matrix API
  * ---------------------------------------------------------------------- */
@@ -867,16 +750,36 @@ extern "C" int b200_spmv_init(int device)
 {
     pthread_mutex_lock(&g_lock);
     ensure_init_locked(device);
+    const int d = default_device_locked();
+    ctx_for_device_locked(d);
+    /* as before: the chosen device is also made current for the caller */
+    CUDA_OK(cudaSetDevice(d));
     pthread_mutex_unlock(&g_lock);
-    return g_device;
+    return d;
+}
+
+static DevCtx *current_ctx_locked(void)
+{
+    ensure_init_locked(-1);
+    int d = 0;
+    CUDA_OK(cudaGetDevice(&d));
+    return ctx_for_device_locked(d);
 }
 
 extern "C" b200_matrix *b200_spmv_upload(const void *a, const int *rowstr, const int *colidx,
                                          int rows, int dtype, int kernel)
 {
     pthread_mutex_lock(&g_lock);
-    ensure_init_locked(-1);
-    b200_matrix *m = upload_locked(a, rowstr, colidx, rows, dtype, kernel);
+    b200_matrix *m = upload_any_locked(current_ctx_locked(), a, rowstr, colidx, rows, dtype, kernel, false);
+    pthread_mutex_unlock(&g_lock);
+    return m;
+}
+
+extern "C" b200_matrix *b200_spmv_upload_device(const void *d_a, const int *d_rowstr, const int *d_colidx,
+                                                int rows, int dtype, int kernel)
+{
+    pthread_mutex_lock(&g_lock);
+    b200_matrix *m = upload_any_locked(current_ctx_locked(), d_a, d_rowstr, d_colidx, rows, dtype, kernel, true);
     pthread_mutex_unlock(&g_lock);
     return m;
 }
@@ -891,9 +794,23 @@ extern "C" void b200_spmv_release(b200_matrix *m)
 extern "C" int b200_spmv_exec(b200_matrix *m, const void *d_x, void *d_y, void *stream)
 {
     if (!m) die("b200_spmv_exec: null matrix");
-    return exec_locked(m, d_x, d_y, (cudaStream_t)stream);
+    DeviceScope scope(m->device);
+    return exec_locked(m, d_x, d_y, (cudaStream_t)stream, nullptr);
 }
 
+extern "C" int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y, void *stream,
+                                     const unsigned long long *flags, unsigned long long epoch,
+                                     int cols_per_rank, int nranks)
+{
+    if (!m) die("b200_spmv_exec_sliced: null matrix");
+    if (!exec_waits_in_kernel(m)) return -1;
+    DeviceScope scope(m->device);
+    SliceFlags sf = {flags, epoch, cols_per_rank, nranks};
+    return exec_locked(m, d_x, d_y, (cudaStream_t)stream, &sf);
+}
+
+extern "C" int b200_spmv_device(const b200_matrix *m) { return m->device; }
+extern "C" int b200_spmv_waits_in_kernel(const b200_matrix *m) { return exec_waits_in_kernel(m) ? 1 : 0; }
 extern "C" int b200_spmv_rows(const b200_matrix *m) { return m->rows; }
 extern "C" int b200_spmv_ncols(const b200_matrix *m) { return m->ncols; }
 extern "C" int64_t b200_spmv_nnz(const b200_matrix *m) { return m->nnz; }
@@ -948,239 +865,4 @@ extern "C" void b200_spmv_partition_rows(const int *rowstr, int rows, int parts,
     }
     bounds[parts] = rows;
 }
-
-/* ------------------------------------------------------------------------
- * drop-in path: cache + per-call x / y movement
- * ---------------------------------------------------------------------- */
-static uint64_t fingerprint(const void *a, const int *rowstr, const int *colidx,
-                            int rows, int64_t nnz, size_t es)
-{
-    /* sampled FNV-1a over 64 probes of each array: cheap mutation detector */
-    uint64_t h = 1469598103934665603ull;
-    const int base = rows > 0 ? rowstr[0] - 1 : 0;
-    const int probes = 16;
-    for (int k = 0; k < probes && nnz > 0; ++k) {
-        const int64_t i = base + (nnz - 1) * k / (probes - 1);
-        uint64_t v = 0;
-        memcpy(&v, (const char *)a + (size_t)i * es, es);
-        h = (h ^ v) * 1099511628211ull;
-        h = (h ^ (uint64_t)(uint32_t)colidx[i]) * 1099511628211ull;
-    }
-    for (int k = 0; k < probes && rows > 0; ++k) {
-        const int64_t i = (int64_t)rows * k / (probes - 1);
-        h = (h ^ (uint64_t)(uint32_t)rowstr[i]) * 1099511628211ull;
-    }
-    return h;
-}
-
-/* Device-usable alias of a pinned (cudaHostAlloc'ed or registered) host range,
- * or NULL for pageable memory. */
-static void *pinned_device_alias(const void *p, size_t bytes)
-{
-    (void)bytes;
-    cudaPointerAttributes attr;
-    cudaError_t e = cudaPointerGetAttributes(&attr, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (attr.type != cudaMemoryTypeHost) return nullptr;
-    return attr.devicePointer;
-}
-
-/* B200_SPMV_PIN_HOST=1: register a caller vector the first time it is seen, so
- * later calls move it by direct access instead of the pinned bounce buffer.
- * Only safe for vectors that outlive the library use (NPB's COMMON arrays,
- * pagerank's two std::vectors); off by default. */
-static void maybe_auto_pin(const void *p, size_t bytes)
-{
-    if (!g_auto_pin || bytes == 0) return;
-    const char *c = (const char *)p;
-    for (const PinnedRange &r : g_pinned)
-        if (c >= r.lo && c + bytes <= r.hi) return;
-    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-        PinnedRange r = {(char *)p, (char *)p + bytes, true};
-        g_pinned.push_back(r);
-    } else {
-        cudaGetLastError();
-    }
-}
-
-static b200_matrix *lookup_locked(const void *a, const int *rowstr, const int *colidx,
-                                  int rows, int dtype)
-{
-    const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - rowstr[0] : 0;
-    ++g_tick;
-    for (CacheEntry &e : g_cache) {
-        if (e.a == a && e.rowstr == rowstr && e.colidx == colidx && e.rows == rows &&
-            e.nnz == nnz && e.dtype == dtype) {
-            const bool tripped = e.guard_slot >= 0 && g_guards[e.guard_slot].tripped;
-            if (tripped || (g_validate &&
-                fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) != e.fingerprint)) {
-                if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
-                guard_disarm(e.guard_slot);
-                release_locked(e.m);
-                e = g_cache.back();
-                g_cache.pop_back();
-                break;
-            }
-            e.last_use = g_tick;
-            return e.m;
-        }
-    }
-    /* miss: upload (evict the least recently used entry beyond the cap) */
-    const double t0 = now_ms();
-    if ((int)g_cache.size() >= g_cache_cap) {
-        size_t victim = 0;
-        for (size_t i = 1; i < g_cache.size(); ++i)
-            if (g_cache[i].last_use < g_cache[victim].last_use) victim = i;
-        guard_disarm(g_cache[victim].guard_slot);
-        release_locked(g_cache[victim].m);
-        g_cache[victim] = g_cache.back();
-        g_cache.pop_back();
-    }
-    CacheEntry e;
-    e.a = a; e.rowstr = rowstr; e.colidx = colidx; e.rows = rows; e.nnz = nnz; e.dtype = dtype;
-    e.fingerprint = g_validate ? fingerprint(a, rowstr, colidx, rows, nnz, elem_size(dtype)) : 0;
-    e.last_use = g_tick;
-    e.m = upload_locked(a, rowstr, colidx, rows, dtype, B200_KERNEL_AUTO);
-    /* staging for the drop-in path */
-    b200_matrix *m = e.m;
-    m->x_bytes = (size_t)std::max(m->ncols, 1) * elem_size(dtype);
-    m->y_bytes = (size_t)std::max(m->rows, 1) * elem_size(dtype);
-    CUDA_OK(cudaMalloc(&m->d_x, m->x_bytes));
-    CUDA_OK(cudaMalloc(&m->d_y, m->y_bytes));
-    CUDA_OK(cudaMallocHost(&m->h_x, m->x_bytes));
-    CUDA_OK(cudaMallocHost(&m->h_y, m->y_bytes));
-    e.guard_slot = guard_arm(a, (size_t)(rows > 0 ? rowstr[rows] - 1 : 0) * elem_size(dtype), rowstr,
-                             ((size_t)rows + 1) * sizeof(int), colidx,
-                             (size_t)(rows > 0 ? rowstr[rows] - 1 : 0) * sizeof(int));
-    g_cache.push_back(e);
-    g_stats.uploads++;
-    g_stats.upload_ms += now_ms() - t0;
-    return m;
-}
-
-static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
-                           const int *colidx, const int *rows, int dtype)
-{
-    pthread_mutex_lock(&g_lock);
-    ensure_init_locked(-1);
-    CUDA_OK(cudaSetDevice(g_device));
-    const int n = *rows;
-    b200_matrix *m = lookup_locked(a, rowstr, colidx, n, dtype);
-    const double t0 = now_ms();
-    if (n > 0) {
-        /* x: host -> device (gpu.c:264).  Pinned caller memory is read straight
-         * over PCIe by a copy kernel on the same stream (no copy-engine hop);
-         * pageable memory goes through the pinned bounce buffer. */
-        maybe_auto_pin(iv, m->x_bytes);
-        maybe_auto_pin(ov, m->y_bytes);
-        if (m->ncols > 0) {
-            const void *x_alias = pinned_device_alias(iv, m->x_bytes);
-            if (x_alias && g_zero_copy) {
-                launch_copy_in(x_alias, m->d_x, m->x_bytes, g_stream);
-            } else if (x_alias) {
-                CUDA_OK(cudaMemcpyAsync(m->d_x, iv, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
-            } else {
-                memcpy(m->h_x, iv, m->x_bytes);
-                if (g_zero_copy) {
-                    void *hx_alias = pinned_device_alias(m->h_x, m->x_bytes);
-                    launch_copy_in(hx_alias, m->d_x, m->x_bytes, g_stream);
-                } else {
-                    CUDA_OK(cudaMemcpyAsync(m->d_x, m->h_x, m->x_bytes, cudaMemcpyHostToDevice, g_stream));
-                }
-            }
-        }
-        if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev0, g_stream));
-        /* y: device -> host (gpu.c:285).  With pinned caller memory the kernel
-         * stores y directly into it; otherwise into the pinned bounce buffer. */
-        void *y_alias = pinned_device_alias(ov, m->y_bytes);
-        const bool y_direct = y_alias != nullptr;
-        void *y_target = nullptr;
-        if (g_zero_copy && m->kernel == B200_KERNEL_PANEL)   /* coalesced y stores only */
-            y_target = y_direct ? y_alias : pinned_device_alias(m->h_y, m->y_bytes);
-        const int launched = exec_locked(m, m->d_x, y_target ? y_target : m->d_y, g_stream);
-        if (g_time_kernels) CUDA_OK(cudaEventRecord(g_ev1, g_stream));
-        if (!y_target)
-            CUDA_OK(cudaMemcpyAsync(y_direct ? ov : m->h_y, m->d_y, m->y_bytes,
-                                    cudaMemcpyDeviceToHost, g_stream));
-        CUDA_OK(cudaStreamSynchronize(g_stream));
-        if (!y_direct) memcpy(ov, m->h_y, m->y_bytes);
-        if (g_time_kernels) {
-            float ms = 0.f;
-            CUDA_OK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
-            g_stats.kernel_ms += ms;
-        }
-        g_stats.kernel_launches += (uint64_t)launched;
-        g_stats.h2d_bytes += m->ncols > 0 ? m->x_bytes : 0;
-        g_stats.d2h_bytes += m->y_bytes;
-    }
-    g_stats.calls++;
-    g_stats.e2e_ms += now_ms() - t0;
-    pthread_mutex_unlock(&g_lock);
-}
-
-extern "C" void *spmv_harness_(double *ov, double *a, double *iv, int *rowstr, int *colidx, int *rows)
-{
-    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F64);
-    return NULL;
-}
-
-extern "C" void *f_spmv_harness_(float *ov, float *a, float *iv, int *rowstr, int *colidx, int *rows)
-{
-    harness_common(ov, a, iv, rowstr, colidx, rows, B200_F32);
-    return NULL;
-}
-
-extern "C" void b200_spmv_invalidate(void)
-{
-    pthread_mutex_lock(&g_lock);
-    for (CacheEntry &e : g_cache) { guard_disarm(e.guard_slot); release_locked(e.m); }
-    g_cache.clear();
-    pthread_mutex_unlock(&g_lock);
-}
-
-extern "C" void b200_spmv_get_stats(b200_spmv_stats *out)
-{
-    pthread_mutex_lock(&g_lock);
-    *out = g_stats;
-    pthread_mutex_unlock(&g_lock);
-}
-
-extern "C" void b200_spmv_reset_stats(void)
-{
-    pthread_mutex_lock(&g_lock);
-    memset(&g_stats, 0, sizeof g_stats);
-    pthread_mutex_unlock(&g_lock);
-}
-
-extern "C" int b200_spmv_pin_host(void *ptr, size_t bytes)
-{
-    pthread_mutex_lock(&g_lock);
-    ensure_init_locked(-1);
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
-    if (e == cudaSuccess) {
-        PinnedRange r = {(char *)ptr, (char *)ptr + bytes, true};
-        g_pinned.push_back(r);
-    } else {
-        cudaGetLastError();
-    }
-    pthread_mutex_unlock(&g_lock);
-    return e == cudaSuccess ? 0 : -1;
-}
-
-extern "C" int b200_spmv_unpin_host(void *ptr)
-{
-    int rc = -1;
-    pthread_mutex_lock(&g_lock);
-    for (size_t i = 0; i < g_pinned.size(); ++i)
-        if (g_pinned[i].lo == (char *)ptr) {
-            cudaHostUnregister(ptr);
-            g_pinned[i] = g_pinned.back();
-            g_pinned.pop_back();
-            rc = 0;
-            break;
-        }
-    pthread_mutex_unlock(&g_lock);
-    return rc;
-}
-
 extern "C" const char *b200_spmv_version(void) { return B200_VERSION; }

@@ -39,6 +39,7 @@ constexpr int NR = B200_PEER_MAX_RANKS;
 struct PeerDev {
     int rank, nranks;
     double *xfull[NR];
+    double *xalt[NR];                   /* second vector buffer: odd epochs of b200_peer_post */
     double *scal[NR];                   /* [B200_PEER_SLOTS][NR] */
     unsigned long long *sflag[NR];      /* [B200_PEER_SLOTS][NR] */
     unsigned long long *vflag[NR];      /* [NR] vector published */
@@ -193,6 +194,36 @@ peer_exchange_kernel(PeerDev g, const double *__restrict__ v, int n, long long l
     }
 }
 
+/* b200_peer_post: the exchange half of a product that waits for its x slices itself
+ * (b200_spmv_exec_sliced).  Epoch e goes to buffer e & 1, which the products of epoch
+ * e - 2 read last: report e - 1 as consumed, wait for every rank's report of e - 2 --
+ * one whole step old, so this hardly ever spins and a slow rank does not hold the
+ * others back --, push the slice, publish e.  Nobody waits for arrivals here. */
+__global__ void __launch_bounds__(kThreads)
+peer_post_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e)
+{
+    if (e > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e - 1);
+    }
+    if (e > 2) wait_flags(g.rflag[g.rank], g.nranks, e - 2);
+    double *const *dstv = (e & 1) ? g.xalt : g.xfull;
+    const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    const int n2 = vec_ok ? n >> 1 : 0;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v);
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
+        const double2 val = v2[i];
+        for (int j = 0; j < g.nranks; ++j)
+            reinterpret_cast<double2 *>(dstv[j] + lo)[i] = val;
+    }
+    for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double val = v[i];
+        for (int j = 0; j < g.nranks; ++j) dstv[j][lo + i] = val;
+    }
+    if (last_block(g.counter + 4) && threadIdx.x == 0)
+        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+}
+
 __global__ void peer_wait_vector_kernel(PeerDev g, unsigned long long e)
 {
     wait_flags(g.vflag[g.rank], g.nranks, e);
@@ -301,7 +332,7 @@ struct b200_peer_group {
 };
 
 static size_t seg_x_bytes(int64_t n) { return (((size_t)n + 2) * sizeof(double) + 255) & ~(size_t)255; }
-static size_t seg_scal_off(int64_t n) { return seg_x_bytes(n); }
+static size_t seg_scal_off(int64_t n) { return 2 * seg_x_bytes(n); }      /* two vector buffers */
 static size_t seg_sflag_off(int64_t n) { return seg_scal_off(n) + B200_PEER_SLOTS * NR * sizeof(double); }
 static size_t seg_vflag_off(int64_t n) { return seg_sflag_off(n) + B200_PEER_SLOTS * NR * sizeof(unsigned long long); }
 static size_t seg_rflag_off(int64_t n) { return seg_vflag_off(n) + NR * sizeof(unsigned long long); }
@@ -314,6 +345,7 @@ static void fill_dev(b200_peer_group *g)
     d.nranks = g->nranks;
     for (int j = 0; j < g->nranks; ++j) {
         d.xfull[j] = (double *)g->peer[j];
+        d.xalt[j] = (double *)(g->peer[j] + seg_x_bytes(g->n_global));
         d.scal[j] = (double *)(g->peer[j] + seg_scal_off(g->n_global));
         d.sflag[j] = (unsigned long long *)(g->peer[j] + seg_sflag_off(g->n_global));
         d.vflag[j] = (unsigned long long *)(g->peer[j] + seg_vflag_off(g->n_global));
@@ -377,6 +409,19 @@ extern "C" void b200_peer_destroy(b200_peer_group *g)
 }
 
 extern "C" double *b200_peer_xfull(b200_peer_group *g) { return (double *)g->local; }
+
+extern "C" double *b200_peer_xbuf(b200_peer_group *g, uint64_t e)
+{
+    return (double *)(g->local + ((e & 1) ? seg_x_bytes(g->n_global) : 0));
+}
+
+extern "C" const unsigned long long *b200_peer_vflags(b200_peer_group *g) { return g->dev.vflag[g->rank]; }
+
+extern "C" void b200_peer_post(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
+                               void *stream)
+{
+    peer_post_kernel<<<kBlocks, kThreads, 0, (cudaStream_t)stream>>>(g->dev, v, n_local, (long long)lo, e);
+}
 
 extern "C" void b200_peer_push(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
                                void *stream)

@@ -55,6 +55,25 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* host side: true when the calling device has been seen before (bit per device ordinal);
+ * used to set function attributes once per device (callers hold the library lock, or
+ * race benignly: setting an attribute twice is harmless) */
+inline bool attr_done(unsigned *mask)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned bit = 1u << (dev & 31);
+    if (*mask & bit) return true;
+    *mask |= bit;
+    return false;
+}
 
 /* loads of the matrix stream: read once.  B200_STREAM_LD selects the cache operator:
  * 1 = ld.global.nc.L1::no_allocate (SASS LDG.E.NA; class C 74.4 us), 0 = ld.global.cs

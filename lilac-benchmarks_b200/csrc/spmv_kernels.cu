@@ -304,6 +304,42 @@ __global__ void copy_in_bytes_kernel(const unsigned char *__restrict__ src,
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
 
+struct CopyDst { unsigned char *p[8]; int n; };
+
+__global__ void copy_in_multi_kernel(const unsigned char *__restrict__ src, CopyDst dst, size_t bytes, int vec)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t done = 0;
+    if (vec) {
+        const size_t n16 = bytes / 16;
+        for (size_t i = t0; i < n16; i += stride) {
+            const int4 v = reinterpret_cast<const int4 *>(src)[i];
+            for (int j = 0; j < dst.n; ++j) reinterpret_cast<int4 *>(dst.p[j])[i] = v;
+        }
+        done = n16 * 16;
+    }
+    for (size_t i = done + t0; i < bytes; i += stride) {
+        const unsigned char v = src[i];
+        for (int j = 0; j < dst.n; ++j) dst.p[j][i] = v;
+    }
+}
+
+void launch_copy_in_multi(const void *src, void *const *dst, int ndst, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0 || ndst <= 0) return;
+    CopyDst d;
+    d.n = ndst > 8 ? 8 : ndst;
+    uintptr_t al = reinterpret_cast<uintptr_t>(src);
+    for (int j = 0; j < d.n; ++j) {
+        d.p[j] = static_cast<unsigned char *>(dst[j]);
+        al |= reinterpret_cast<uintptr_t>(dst[j]);
+    }
+    const int grid = (int)std::min<size_t>((bytes / 16 + 255) / 256 + 1, 148 * 4);
+    copy_in_multi_kernel<<<grid, 256, 0, s>>>(static_cast<const unsigned char *>(src), d, bytes,
+                                              (al & 15) == 0 ? 1 : 0);
+}
+
 void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s)
 {
     if (bytes == 0) return;

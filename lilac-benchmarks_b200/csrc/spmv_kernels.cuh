@@ -55,6 +55,9 @@ int tile_elems(bool f32);
 /* dst[0..bytes) = src[0..bytes): src is a device alias of pinned host memory,
  * so the loads travel over PCIe; runs on the SMs, in stream order */
 void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s);
+/* the same with up to 8 destinations (the local buffer and the peers' over NVLink):
+ * the source is read once.  All pointers 16-byte aligned relative to each other. */
+void launch_copy_in_multi(const void *src, void *const *dst, int ndst, size_t bytes, cudaStream_t s);
 
 /* ------------------------------------------------------------------------
  * PANEL: private column-panel layout (built once at upload, on the device);
@@ -103,9 +106,19 @@ template <typename T>
 void launch_panelg_fill(const T *val, const int *col, const int *rowptr, int rows,
                         const DevPanel &pm, const uint16_t *seglen, unsigned char *stream_out,
                         cudaStream_t s);
-/* ... and its kernel: the matrix stream through per-warp shared-memory rings (spmv_panelr.cu) */
+/* x that arrives slice by slice from other GPUs (include/b200_peer.h): flags[r] >= epoch
+ * <=> columns [r * cols_per_rank, (r + 1) * cols_per_rank) are in the buffer.  flags == NULL:
+ * x is complete when the kernel starts. */
+struct XFlags {
+    const unsigned long long *flags;
+    unsigned long long epoch;
+    int cols_per_rank;
+    int nranks;
+};
+/* ... and its kernel: the matrix stream through per-warp shared-memory rings (spmv_panelr.cu);
+ * waits per x slice on `xf` before it requests the panels that need the slice */
 template <typename T>
-void launch_panelr(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
+void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s);
 size_t panelr_smem_bytes(const DevPanel &pm, bool f32);
 
 /* ------------------------------------------------------------------------

@@ -390,12 +390,10 @@ size_t panel_smem_bytes(const DevPanel &pm, bool f32)
 template <typename T, int U, int MAXT>
 static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned attr_set = 0;                  /* function attributes are per device */
+    if (!attr_done(&attr_set))
         cudaFuncSetAttribute(spmv_panel_kernel<T, U, MAXT>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
     const size_t smem = panel_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panel_kernel<T, U, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(

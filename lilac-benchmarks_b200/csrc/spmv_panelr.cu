@@ -96,6 +96,9 @@ __device__ __forceinline__ void consume_rows(const unsigned char *rows, int lane
     }
 }
 
+#ifndef B200_RING_WAR_FENCE
+#define B200_RING_WAR_FENCE 0
+#endif
 #ifndef B200_XCOPY_BYTES
 #define B200_XCOPY_BYTES 262144
 #endif
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 spmv_panelr_kernel(const unsigned char *__restrict__ stream,
                    const uint16_t *__restrict__ rowids, const int *__restrict__ slice_off,
                    const T *__restrict__ x, T *__restrict__ y,
-                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S)
+                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S, XFlags xf)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -157,14 +160,29 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
     if (lane == 0)
         for (int t = 0; t < S && t < nstage; ++t) issue_stage(t, t);
 
+    /* x assembled from the slices of several GPUs: the slices a panel needs must have
+     * arrived (epoch flag written with st.release.sys by the pushing rank after its stores)
+     * before the panel is requested.  Columns are walked left to right, so `rank_ready`
+     * only grows; the product overlaps the exchange instead of running after it. */
+    int rank_ready = 0;                                   /* ranks [0, rank_ready) have arrived */
+    auto wait_slices = [&](int cbase, int cw) {           /* one thread */
+        const int r1 = min((cbase + cw - 1) / xf.cols_per_rank, xf.nranks - 1);
+        if (r1 < rank_ready) return;
+        for (; rank_ready <= r1; ++rank_ready)
+            while (ld_acquire_sys_u64(xf.flags + rank_ready) < xf.epoch) { }
+        /* the slice was written through the generic proxy (by other GPUs), the bulk copy
+         * reads it through the async proxy */
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+    };
     auto issue_panel = [&](int p) {                       /* thread 0 only (TMA path) */
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
         constexpr int VE = 16 / sizeof(T);
         const int cw_al = cw & ~(VE - 1);
+        if (xf.flags) wait_slices(cbase, cw);
         if (cw_al < cw) {                                 /* ragged tail: generic stores, then the fence */
-            for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);
+            for (int i = cw_al; i < cw; ++i) dst[i] = __ldcg(x + cbase + i);
             fence_proxy_async();
         }
         uint64_t *bar = &xbars[p & (nbuf - 1)];
@@ -184,7 +202,11 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
-        for (int i = tid; i < cw; i += Tn) dst[i] = __ldg(x + cbase + i);
+        if (xf.flags) {                                   /* block-uniform */
+            if (tid == 0) wait_slices(cbase, cw);
+            __syncthreads();
+        }
+        for (int i = tid; i < cw; i += Tn) dst[i] = __ldcg(x + cbase + i);
     };
     if (use_tma) {
         if (tid == 0) issue_panel(0);
@@ -249,7 +271,18 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
                 /* every lane has used its values of the stage (they fed arithmetic), so the
                  * slot can be overwritten: same hand-over as an "empty" mbarrier arrive */
                 __syncwarp();
-                if (lane == 0 && t_cur + S < nstage) issue_stage(t_cur + S, slot);
+                if (lane == 0 && t_cur + S < nstage) {
+                    /* Write-after-read across proxies: the generic-proxy reads of the slot have
+                     * returned their data (it fed arithmetic) and __syncwarp orders them before
+                     * this thread, so the bulk copy cannot overtake them -- the same hand-over
+                     * as a consumer's arrive on an "empty" mbarrier, which CUTLASS pipelines do
+                     * not fence either.  The explicit proxy fence costs 3 % of the kernel
+                     * (profiles/r02_run2: class D 1/8 block 277 us against 269 us). */
+#if B200_RING_WAR_FENCE
+                    fence_proxy_async();
+#endif
+                    issue_stage(t_cur + S, slot);
+                }
                 ++t_cur;
                 sr = 0;
                 if (++slot == S) { slot = 0; par ^= 1u; }
@@ -280,43 +313,41 @@ size_t panelr_smem_bytes(const DevPanel &pm, bool f32)
 }
 
 template <typename T, int G, int K, int MAXT>
-static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned attr_set = 0;                  /* function attributes are per device */
+    if (!attr_done(&attr_set))
         cudaFuncSetAttribute(spmv_panelr_kernel<T, G, K, MAXT>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
     const size_t smem = panelr_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panelr_kernel<T, G, K, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const unsigned char *>(pm.val), pm.rowids, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S);
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S, xf);
 }
 
 template <typename T, int G>
-static void launch_panelr_g(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+static void launch_panelr_g(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
 {
     const int threads = pm.R / pm.G;
     if (threads > 512) {
-        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 768>(pm, x, y, s);
-        else                launch_panelr_cfg<T, G, 4, 768>(pm, x, y, s);
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 768>(pm, x, y, xf, s);
+        else                launch_panelr_cfg<T, G, 4, 768>(pm, x, y, xf, s);
     } else {
-        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 512>(pm, x, y, s);
-        else                launch_panelr_cfg<T, G, 4, 512>(pm, x, y, s);
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 512>(pm, x, y, xf, s);
+        else                launch_panelr_cfg<T, G, 4, 512>(pm, x, y, xf, s);
     }
 }
 
 template <typename T>
-void launch_panelr(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
-    if (pm.G == 2)      launch_panelr_g<T, 2>(pm, x, y, s);
-    else if (pm.G == 4) launch_panelr_g<T, 4>(pm, x, y, s);
-    else                launch_panelr_g<T, 8>(pm, x, y, s);
+    if (pm.G == 2)      launch_panelr_g<T, 2>(pm, x, y, xf, s);
+    else if (pm.G == 4) launch_panelr_g<T, 4>(pm, x, y, xf, s);
+    else                launch_panelr_g<T, 8>(pm, x, y, xf, s);
 }
-template void launch_panelr<double>(const DevPanel &, const double *, double *, cudaStream_t);
-template void launch_panelr<float>(const DevPanel &, const float *, float *, cudaStream_t);
+template void launch_panelr<double>(const DevPanel &, const double *, double *, const XFlags &, cudaStream_t);
+template void launch_panelr<float>(const DevPanel &, const float *, float *, const XFlags &, cudaStream_t);
 
 }  // namespace b200

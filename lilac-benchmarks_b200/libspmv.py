@@ -26,6 +26,12 @@ class CgResult(C.Structure):
                 ("spmv_launches", c_int), ("vector_launches", c_int)]
 
 
+class NpbDeviceCsr(C.Structure):
+    """b200_npb_csr of include/b200_npb.h."""
+    _fields_ = [("rows", c_int), ("nnz", c_int64), ("d_rowstr", c_void_p), ("d_colidx", c_void_p),
+                ("d_a", c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("calls", c_uint64), ("uploads", c_uint64), ("kernel_launches", c_uint64),
                 ("kernel_ms", c_double), ("e2e_ms", c_double), ("upload_ms", c_double),
@@ -57,6 +63,17 @@ def lib():
     L.b200_spmv_release.restype = None
     L.b200_spmv_exec.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_spmv_exec.restype = c_int
+    L.b200_spmv_exec_sliced.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64,
+                                        c_int, c_int]
+    L.b200_spmv_exec_sliced.restype = c_int
+    L.b200_spmv_upload_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
+    L.b200_spmv_upload_device.restype = c_void_p
+    L.b200_spmv_device.argtypes = [c_void_p]
+    L.b200_spmv_device.restype = c_int
+    L.b200_spmv_waits_in_kernel.argtypes = [c_void_p]
+    L.b200_spmv_waits_in_kernel.restype = c_int
+    L.b200_spmv_devices_in_use.argtypes = []
+    L.b200_spmv_devices_in_use.restype = c_int
     for name, res in (("rows", c_int), ("ncols", c_int), ("nnz", c_int64), ("kernel", c_int),
                       ("kernel_name", c_char_p), ("launches_per_exec", c_int),
                       ("algorithmic_bytes", c_int64), ("resident_bytes", c_int64)):
@@ -94,6 +111,14 @@ def lib():
     L.b200_cg_update_p.restype = None
     L.b200_cg_finish.argtypes = [c_void_p, c_void_p, c_void_p]
     L.b200_cg_finish.restype = None
+    # include/b200_npb.h
+    L.b200_npb_makea_device.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                        c_double, c_int, c_int, POINTER(NpbDeviceCsr)]
+    L.b200_npb_makea_device.restype = c_int
+    L.b200_npb_csr_free.argtypes = [POINTER(NpbDeviceCsr)]
+    L.b200_npb_csr_free.restype = None
+    L.b200_npb_csr_to_host.argtypes = [POINTER(NpbDeviceCsr), ip, ip, dp]
+    L.b200_npb_csr_to_host.restype = c_int
     # include/b200_peer.h
     u64 = C.c_uint64
     L.b200_peer_create.argtypes = [c_int, c_int, c_int64, c_void_p]
@@ -116,6 +141,12 @@ def lib():
                                      u64, c_void_p]
     L.b200_peer_scale.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, u64, c_void_p]
     L.b200_peer_read_slots.argtypes = [c_void_p, POINTER(c_int), POINTER(u64), c_int, c_void_p, c_void_p]
+    L.b200_peer_post.argtypes = [c_void_p, c_void_p, c_int, c_int64, u64, c_void_p]
+    L.b200_peer_post.restype = None
+    L.b200_peer_xbuf.argtypes = [c_void_p, u64]
+    L.b200_peer_xbuf.restype = c_void_p
+    L.b200_peer_vflags.argtypes = [c_void_p]
+    L.b200_peer_vflags.restype = c_void_p
     for nm in ("push", "push_after", "consumed", "wait_vector", "dot", "update_zr", "update_p", "scale", "read_slots"):
         getattr(L, "b200_peer_" + nm).restype = None
     _lib = L
@@ -173,6 +204,11 @@ def invalidate():
     lib().b200_spmv_invalidate()
 
 
+def devices_in_use():
+    """Most devices any matrix cached by the drop-in symbols is spread over."""
+    return lib().b200_spmv_devices_in_use()
+
+
 def partition_rows(rowstr, parts):
     """nnz-balanced contiguous row partition: parts+1 boundaries (0-based rows)."""
     _check(rowstr, np.int32, "rowstr")
@@ -204,6 +240,25 @@ class ResidentMatrix:
                                          KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel))
         if not self._h:
             raise RuntimeError("b200_spmv_upload failed")
+        self._describe()
+
+    @classmethod
+    def from_device(cls, d_a, d_rowstr, d_colidx, rows, np_dtype=np.float64, kernel="auto", keep=None):
+        """Upload from DEVICE arrays (raw pointers as ints) of the current device; same 1-based
+        contents as the ABI.  `keep` holds whatever owns that memory until the upload is done."""
+        self = cls.__new__(cls)
+        self.dtype, self.np_dtype = (F64, np.float64) if np_dtype == np.float64 else (F32, np.float32)
+        self._keep = keep
+        self._h = lib().b200_spmv_upload_device(c_void_p(d_a), c_void_p(d_rowstr), c_void_p(d_colidx),
+                                                int(rows), self.dtype,
+                                                KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel))
+        if not self._h:
+            raise RuntimeError("b200_spmv_upload_device failed")
+        self._describe()
+        self._keep = None
+        return self
+
+    def _describe(self):
         L = lib()
         self.rows = L.b200_spmv_rows(self._h)
         self.ncols = L.b200_spmv_ncols(self._h)
@@ -212,6 +267,14 @@ class ResidentMatrix:
         self.launches_per_exec = L.b200_spmv_launches_per_exec(self._h)
         self.algorithmic_bytes = L.b200_spmv_algorithmic_bytes(self._h)
         self.resident_bytes = L.b200_spmv_resident_bytes(self._h)
+        self.device = L.b200_spmv_device(self._h)
+        self.waits_in_kernel = bool(L.b200_spmv_waits_in_kernel(self._h))
+
+    def exec_sliced_ptr(self, d_x, d_y, stream, flags, epoch, cols_per_rank, nranks):
+        """Product on an x that is still arriving slice by slice (include/b200_peer.h);
+        returns -1 without launching if this matrix's kernel cannot wait in-kernel."""
+        return lib().b200_spmv_exec_sliced(self._h, c_void_p(d_x), c_void_p(d_y), c_void_p(stream),
+                                           c_void_p(flags), int(epoch), int(cols_per_rank), int(nranks))
 
     def exec_ptr(self, d_x, d_y, stream=0):
         """Launch on raw device pointers (ints) and a cudaStream_t handle (int)."""

@@ -53,6 +53,11 @@ def lib():
                                           POINTER(POINTER(c_double)), c_int, POINTER(c_int),
                                           POINTER(c_int), c_int, c_int]
         L.npb_time_spmv_calls.restype = c_double
+        L.npb_vectors_get.argtypes = [POINTER(CgClass), POINTER(c_void_p), POINTER(c_void_p),
+                                      POINTER(c_void_p), POINTER(c_void_p)]
+        L.npb_vectors_get.restype = c_int
+        L.npb_free.argtypes = [c_void_p]
+        L.npb_free.restype = None
         L.npb_randlc.argtypes = [POINTER(c_double), c_double]
         L.npb_randlc.restype = c_double
         _lib = L
@@ -119,6 +124,68 @@ class NpbMatrix:
         csr.colidx = self.colidx.ctypes.data_as(POINTER(c_int))
         csr.a = self.a.ctypes.data_as(POINTER(c_double))
         return csr
+
+
+class NpbDeviceMatrix:
+    """Rows [row_lo, row_hi) of an NPB CG class assembled ON the current CUDA device
+    (include/b200_npb.h): the host only draws the generating vectors (the sequential
+    random stream of cg.f:709-718), the rows are built by the GPU, bit for bit what
+    `NpbMatrix` builds on the host.  Device pointers are plain ints."""
+
+    def __init__(self, letter, row_lo=None, row_hi=None, release_vectors=True):
+        from . import libspmv
+        self.cls = cg_class(letter)
+        if row_lo is None:
+            row_lo, row_hi = 0, self.cls.na
+        arow, acol, aelt, size = c_void_p(), c_void_p(), c_void_p(), c_void_p()
+        if lib().npb_vectors_get(C.byref(self.cls), C.byref(arow), C.byref(acol), C.byref(aelt),
+                                 C.byref(size)) != 0:
+            raise RuntimeError("npb_vectors_get failed")
+        self._L = libspmv.lib()
+        self._csr = libspmv.NpbDeviceCsr()
+        try:
+            rc = self._L.b200_npb_makea_device(self.cls.na, self.cls.nonzer + 1, arow, acol, aelt, size,
+                                               self.cls.rcond, self.cls.shift, int(row_lo), int(row_hi),
+                                               C.byref(self._csr))
+        finally:
+            lib().npb_free(size)
+            if release_vectors:
+                lib().npb_makea_release_cache()
+        if rc == -1:
+            raise RuntimeError("row block exceeds the int32 ABI; use more ranks")
+        if rc != 0:
+            raise RuntimeError(f"b200_npb_makea_device failed with {rc}")
+        self.n = row_hi - row_lo
+        self.row_lo, self.row_hi = row_lo, row_hi
+        self.nnz = int(self._csr.nnz)
+
+    def resident(self, kernel="auto"):
+        """Upload device -> device and keep resident (b200_spmv_upload_device)."""
+        from . import libspmv
+        return libspmv.ResidentMatrix.from_device(self._csr.d_a, self._csr.d_rowstr, self._csr.d_colidx,
+                                                  self.n, kernel=kernel, keep=self)
+
+    def to_host(self):
+        """(a, rowstr, colidx) as numpy arrays, for the CPU checker."""
+        rowstr = np.empty(self.n + 1, dtype=np.int32)
+        colidx = np.empty(max(self.nnz, 1), dtype=np.int32)
+        a = np.empty(max(self.nnz, 1), dtype=np.float64)
+        rc = self._L.b200_npb_csr_to_host(C.byref(self._csr), rowstr.ctypes.data_as(POINTER(c_int)),
+                                          colidx.ctypes.data_as(POINTER(c_int)),
+                                          a.ctypes.data_as(POINTER(c_double)))
+        if rc != 0:
+            raise RuntimeError(f"b200_npb_csr_to_host failed with {rc}")
+        return a[:self.nnz], rowstr, colidx[:self.nnz]
+
+    def free(self):
+        if self._csr.d_rowstr:
+            self._L.b200_npb_csr_free(C.byref(self._csr))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def run_cg(matrix, harness_addr, verbose=False):

@@ -347,13 +347,19 @@ class PeerNpbCg:
 
 
 class PeerShardedSpmv:
-    """y_local = A[rows of this rank, :] @ x with the exchange done by this
-    rank's own push kernel over NVLink peer memory (include/b200_peer.h) instead
-    of an NCCL allgather: one exchange kernel (report the previous vector as
-    consumed, wait for every rank's report, push my slice into every rank's x
-    buffer, publish, wait for everybody's flag), then the local kernel."""
+    """y_local = A[rows of this rank, :] @ x with the exchange done by this rank's own
+    kernels over NVLink peer memory (include/b200_peer.h) instead of an NCCL allgather.
 
-    def __init__(self, libspmv_module, resident_matrix, layout, rank, dist=None, device="cuda"):
+    Overlapped form (the RING kernel): `b200_peer_post` pushes my slice into every
+    rank's buffer of this epoch (two buffers alternate, so nobody waits for a slow
+    rank's previous product) and publishes the epoch; the product then waits per slice,
+    just before the column panels that need it (`b200_spmv_exec_sliced`), i.e. it starts
+    on the slices that have arrived while the others are still in flight.
+    Other kernels: one exchange kernel that also waits for every rank's slice, then the
+    product."""
+
+    def __init__(self, libspmv_module, resident_matrix, layout, rank, dist=None, device="cuda",
+                 overlap=True):
         import ctypes as C
         import torch
         self.torch = torch
@@ -374,15 +380,30 @@ class PeerShardedSpmv:
                 raise RuntimeError("b200_peer_connect failed")
             dist.barrier()
         self.xfull = self.L.b200_peer_xfull(self.g)
+        self.vflags = self.L.b200_peer_vflags(self.g)
         self.y_local = torch.zeros(self.hi - self.lo, dtype=torch.float64, device=device)
         self.epoch = 0
+        # every rank must take the same branch: the overlapped form needs a kernel that can
+        # wait in-kernel on every rank and slices that are whole multiples of `slot` columns
+        ok = 1 if (overlap and resident_matrix.waits_in_kernel and layout.contiguous) else 0
+        if dist is not None and world > 1:
+            t = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        self.overlap = bool(ok)
 
     def step(self, x_local):
         s = self.torch.cuda.current_stream().cuda_stream
         self.epoch += 1
-        # one launch: consumed(previous) -> wait -> push -> publish -> wait for everybody
-        self.L.b200_peer_exchange(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, self.epoch, s)
-        self.rm.exec_ptr(self.xfull, self.y_local.data_ptr(), s)
+        e = self.epoch
+        if self.overlap:
+            self.L.b200_peer_post(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, e, s)
+            self.rm.exec_sliced_ptr(self.L.b200_peer_xbuf(self.g, e), self.y_local.data_ptr(), s,
+                                    self.vflags, e, self.layout.slot, self.layout.parts)
+        else:
+            # one launch: consumed(previous) -> wait -> push -> publish -> wait for everybody
+            self.L.b200_peer_exchange(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, e, s)
+            self.rm.exec_ptr(self.xfull, self.y_local.data_ptr(), s)
         return self.y_local
 
     def close(self):

@@ -513,3 +513,173 @@ def test_peer_exchange_spmv_single_rank_group(libspmv, oracle, npb):
             assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx))
     finally:
         sh.close()
+
+
+@pytest.mark.parametrize("cls", ["W", "A"])
+def test_caller_pinned_vectors_through_the_abi(libspmv, oracle, npb, cls):
+    """The e2e headline path: x read in place over PCIe from the caller's pinned vector,
+    y stored by the kernel straight into the caller's pinned vector (b200_dropin.cu);
+    mixed cases too (only x pinned, only y pinned, x at an odd offset inside a pinned
+    allocation)."""
+    import torch
+    m = npb.NpbMatrix(cls)
+    rng = np.random.default_rng(5)
+    for x_pinned, y_pinned, off in ((True, True, 0), (True, False, 0), (False, True, 0), (True, True, 3)):
+        x = rng.standard_normal(m.n + 2 + off)
+        y = np.full(m.n, np.nan)
+        keep = []
+        if x_pinned:
+            keep.append(torch.from_numpy(x).pin_memory())
+            x = keep[-1].numpy()
+        if y_pinned:
+            keep.append(torch.from_numpy(y).pin_memory())
+            y = keep[-1].numpy()
+        xv = x[off:]
+        libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
+        assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx)), (x_pinned, y_pinned, off)
+    assert libspmv.stats()["uploads"] >= 1
+
+
+def test_vector_that_is_only_partly_pinned_takes_the_bounce_buffer(libspmv, oracle, npb):
+    """a range that is pinned only at its start must not be treated as
+    device-accessible (the copy kernel would fault on the pageable tail)."""
+    m = npb.NpbMatrix("W")
+    rng = np.random.default_rng(6)
+    buf = rng.standard_normal(m.n + 2 + 1024)
+    base = buf.ctypes.data
+    lo = (base + 4095) // 4096 * 4096                   # first whole page inside the buffer
+    first = (lo - base) // 8
+    xv = buf[first:first + m.n + 2]                     # starts exactly on the pinned page ...
+    half = (m.n // 2) * 8 // 4096 * 4096                # ... but only its first half is pinned
+    assert xv.ctypes.data == lo and half > 0
+    assert libspmv.lib().b200_spmv_pin_host(lo, half) == 0
+    try:
+        for target_pinned_too in (False, True):
+            ybuf = np.zeros(m.n + 1024)
+            ybase = ybuf.ctypes.data
+            ylo = (ybase + 4095) // 4096 * 4096
+            y = ybuf[(ylo - ybase) // 8:(ylo - ybase) // 8 + m.n]
+            if target_pinned_too:
+                assert libspmv.lib().b200_spmv_pin_host(ylo, half) == 0
+            try:
+                libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
+                assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx))
+            finally:
+                if target_pinned_too:
+                    assert libspmv.lib().b200_spmv_unpin_host(ylo) == 0
+    finally:
+        assert libspmv.lib().b200_spmv_unpin_host(lo) == 0
+
+
+PIN_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+from lilac_benchmarks_b200 import libspmv, npb
+m = npb.NpbMatrix("A")
+# whole NPB CG with B200_SPMV_PIN_HOST=1: the caller's pageable vectors are registered on
+# first sight and then read / written in place
+gpu = npb.run_cg(m, libspmv.harness_address())
+cpu = npb.run_cg(m, oracle.harness_address())
+assert gpu["verified"] and np.array_equal(gpu["zeta_hist"], cpu["zeta_hist"])
+assert np.array_equal(gpu["rnorm_hist"], cpu["rnorm_hist"])
+rng = np.random.default_rng(1)
+x = rng.standard_normal(m.n + 2); y = np.zeros(m.n)
+for _ in range(3):
+    x[:] = rng.standard_normal(m.n + 2)
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx))
+print("pin ok")
+"""
+
+
+def test_auto_pin_host_env(tmp_path):
+    """B200_SPMV_PIN_HOST=1 through the whole NPB CG class A run."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "pin.py"
+    script.write_text(PIN_SCRIPT.format(root=root))
+    env = dict(os.environ, B200_SPMV_PIN_HOST="1")
+    proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "pin ok" in proc.stdout, proc.stdout[-3000:]
+
+
+def test_guard_is_on_by_default_and_catches_in_place_edits(libspmv, oracle):
+    """libspmv/gpu.c:236-262 protects the host arrays whenever a matrix is resident; so does
+    this library by default.  An edit of ONE value the sampled fingerprint does not probe
+    must still be seen."""
+    rng = np.random.default_rng(12)
+    n, ncols = 20000, 9000
+    a, c, rowstr, x = make_csr(rng, n, ncols, rng.poisson(30, n))
+    y = np.zeros(n)
+    libspmv.spmv_harness(y, a, x, rowstr, c, n)
+    up0 = libspmv.stats()["uploads"]
+    a[len(a) // 2 + 12345] += 1.0                   # not on a probe position
+    libspmv.spmv_harness(y, a, x, rowstr, c, n)
+    assert libspmv.stats()["uploads"] == up0 + 1
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+    c[7777] = 1
+    libspmv.spmv_harness(y, a, x, rowstr, c, n)
+    assert libspmv.stats()["uploads"] == up0 + 2
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+
+
+def test_zero_based_offsets_are_refused():
+    """rowstr[0] < 1 would read in front of the arrays; the library aborts with a
+    message instead (no error channel in the ABI: libspmv/gpu.c:42-80 asserts)."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    code = (f"import sys; sys.path.insert(0, {root!r}); import numpy as np; import __graft_entry__ as e; "
+            "e.load_package(); from lilac_benchmarks_b200 import libspmv; "
+            "rs = np.array([0, 2, 4], dtype=np.int32); c = np.array([1, 2, 1, 2], dtype=np.int32); "
+            "a = np.ones(4); x = np.ones(2); y = np.zeros(2); libspmv.spmv_harness(y, a, x, rs, c, 2)")
+    proc = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                          text=True, timeout=300)
+    assert proc.returncode != 0 and "row offsets are 1-based" in proc.stderr, proc.stderr[-2000:]
+
+
+def test_upload_from_device_arrays(libspmv, oracle, npb):
+    """b200_spmv_upload_device: the same matrix from DEVICE arrays gives the same bits."""
+    import torch
+    m = npb.NpbMatrix("W")
+    da, dr, dc = (torch.from_numpy(v).cuda() for v in (m.a, m.rowstr, m.colidx))
+    rm = libspmv.ResidentMatrix.from_device(da.data_ptr(), dr.data_ptr(), dc.data_ptr(), m.n, keep=(da, dr, dc))
+    assert rm.nnz == m.nnz and rm.ncols == m.n
+    x = np.random.default_rng(2).standard_normal(m.n)
+    dy = torch.empty(m.n, dtype=torch.float64, device="cuda")
+    rm.exec(torch.from_numpy(x).cuda(), dy)
+    assert np.array_equal(dy.cpu().numpy(), oracle.spmv(m.a, x, m.rowstr, m.colidx))
+
+
+@pytest.mark.parametrize("cls,blocks", [("S", 1), ("W", 3), ("A", 1), ("B", 4)])
+def test_device_makea_bit_identical_to_the_host_generator(libspmv, oracle, npb, cls, blocks):
+    """include/b200_npb.h: the NPB matrix assembled on the GPU equals the host generator's
+    (callers/npb/makea.c, itself pinned to the SNU CG histories and nnz self-checks) bit
+    for bit -- row pointers, columns and values -- for whole matrices and row blocks."""
+    import torch
+    whole = npb.NpbMatrix(cls)
+    na = whole.n
+    cuts = [na * k // blocks for k in range(blocks + 1)]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        dm = npb.NpbDeviceMatrix(cls, lo, hi)
+        a, rowstr, colidx = dm.to_host()
+        ref = npb.NpbMatrix(cls, lo, hi) if blocks > 1 else whole
+        assert dm.nnz == ref.nnz
+        assert np.array_equal(rowstr, ref.rowstr) and np.array_equal(colidx, ref.colidx)
+        assert np.array_equal(a, ref.a)
+        # and it feeds the resident-matrix API without touching the host
+        rm = dm.resident()
+        x = np.random.default_rng(lo).standard_normal(na)
+        dy = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+        rm.exec(torch.from_numpy(x).cuda(), dy)
+        assert np.array_equal(dy.cpu().numpy(), oracle.spmv(ref.a, x, ref.rowstr, ref.colidx))
+        rm.release()
+        dm.free()

@@ -92,3 +92,58 @@ def test_pagerank_bit_identical_on_gpu(callers, gen, oracle, libspmv):
     assert np.allclose(gpu, cpu, rtol=1e-12, atol=0)
     if short.all():
         assert np.array_equal(gpu, cpu) and e0 == e1
+
+
+def _split_by_cap(rowstr, cap):
+    lens = np.diff(rowstr)
+    return lens <= cap
+
+
+@pytest.mark.gpu
+def test_crsmat170u_full_size_elementwise(gen, oracle, libspmv):
+    """BASELINE config 3 at size: big_gen.py's 170^3 matrix (4.9 M rows, 24 M nonzeros,
+    unsorted stream windows) through spmv_harness_, every y element against the OpenMP
+    oracle.  Rows are short (<= 25), so every row is inside the order-preserving tiles:
+    bit-exact."""
+    libspmv.invalidate()
+    a, colidx, rowstr, n = gen.crsmat(170)
+    assert n == 170 ** 3 and np.diff(rowstr).max() <= 64
+    rng = np.random.default_rng(170)
+    for x in (np.ones(n), rng.standard_normal(n)):
+        y = np.full(n, np.nan)
+        libspmv.spmv_harness(y, a, x, rowstr, colidx, n)
+        assert np.array_equal(y, oracle.spmv(a, x, rowstr, colidx, omp=True))
+    libspmv.invalidate()
+
+
+@pytest.mark.gpu
+def test_powerlaw_2_22_full_size_elementwise(gen, oracle, libspmv):
+    """BASELINE config 4 at size: the 2^22-vertex power-law graph with NO cap on the row
+    lengths (rows up to 65536 entries go through the nnz-split long-row path).  Rows inside
+    the order-preserving tiles: bit-exact; the long rows re-order the sum and are held to
+    the north star's 1e-12 relative (pagerank values are positive: no cancellation)."""
+    import torch
+    libspmv.invalidate()
+    a, colidx, rowstr, x0 = gen.powerlaw_graph()
+    n = len(rowstr) - 1
+    assert n == 1 << 22 and np.diff(rowstr).max() >= 30000
+    rm = libspmv.ResidentMatrix(a, rowstr, colidx)
+    dy = torch.empty(n, dtype=torch.float64, device="cuda")
+    rm.exec(torch.from_numpy(x0).cuda(), dy)
+    y = dy.cpu().numpy()
+    y0 = oracle.spmv(a, x0, rowstr, colidx, omp=True)
+    lens = np.diff(rowstr)
+    tiled = lens <= 32                      # certainly below the cap (2.5 x mean = 40)
+    assert np.array_equal(y[tiled], y0[tiled])
+    assert np.all(np.abs(y - y0) <= 1e-12 * np.abs(y0))
+    # and one pagerank step through the ABI with the C caller
+    x1_cpu, _, _ = callers_pagerank(a, rowstr, colidx, x0, oracle.harness_address())
+    x1_gpu, _, _ = callers_pagerank(a, rowstr, colidx, x0, libspmv.harness_address())
+    assert np.all(np.abs(x1_gpu - x1_cpu) <= 1e-12 * np.abs(x1_cpu))
+    rm.release()
+    libspmv.invalidate()
+
+
+def callers_pagerank(a, rowstr, colidx, x0, addr):
+    from lilac_benchmarks_b200 import callers
+    return callers.pagerank(a, rowstr, colidx, x0, addr, iters=1)
