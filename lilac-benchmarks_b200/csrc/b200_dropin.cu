@@ -19,7 +19,10 @@
  *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but pinned caller
  *                          vectors are read / written in place over PCIe by the
  *                          kernels, pageable ones go through pinned bounce buffers
- *                          filled by a small pool of copy threads.
+ *                          (a pool of copy threads for the two memcpy's was measured
+ *                          and dropped: waking sleeping helpers costs more than the
+ *                          75 us copy, NPB CG class C went from 1.34 s to 2.06 s,
+ *                          profiles/r02_run3_bench_C.json).
  *   single device          gpu.c drives one GPU.  With B200_SPMV_DEVICES=0,1,..
  *                          (or "all") the SAME two symbols drive several: the rows
  *                          are split into nnz-balanced blocks, one per device;
@@ -40,7 +43,6 @@
 #include <unistd.h>
 
 #include <algorithm>
-#include <atomic>
 #include <vector>
 
 using namespace b200;
@@ -177,73 +179,6 @@ static void guard_disarm(int slot)
     for (int j = 0; j < 3; ++j)
         if (g.r[j].lo) mprotect(g.r[j].lo, (size_t)(g.r[j].hi - g.r[j].lo), PROT_READ | PROT_WRITE);
     g.used = 0;
-}
-
-/* ------------------------------------------------------------------------
- * copy threads: pageable caller vectors go through pinned bounce buffers, and one
- * core copies 1.2 MB (NPB class C) in ~75 us -- as long as the product itself.
- * A few helper threads (B200_SPMV_COPY_THREADS, default 4 including the caller)
- * split copies of >= 256 KB.  They sleep on a condition variable between calls.
- * ---------------------------------------------------------------------- */
-struct CopyPool {
-    pthread_mutex_t mu;
-    pthread_cond_t cv;
-    int nworkers;
-    uint64_t generation;
-    char *dst; const char *src; size_t bytes; int nsplit;
-    std::atomic<int> pending;
-    bool started;
-};
-static CopyPool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, nullptr, nullptr, 0, 0, {0}, false};
-
-static void copy_share(char *dst, const char *src, size_t bytes, int nsplit, int k)
-{
-    const size_t unit = 4096;
-    const size_t per = ((bytes + (size_t)nsplit - 1) / nsplit + unit - 1) / unit * unit;
-    const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
-    if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
-}
-
-static void *copy_worker(void *arg)
-{
-    const int id = (int)(intptr_t)arg;            /* 1 .. nworkers */
-    uint64_t seen = 0;
-    pthread_mutex_lock(&g_pool.mu);
-    for (;;) {
-        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv, &g_pool.mu);
-        seen = g_pool.generation;
-        char *dst = g_pool.dst; const char *src = g_pool.src;
-        const size_t bytes = g_pool.bytes; const int nsplit = g_pool.nsplit;
-        pthread_mutex_unlock(&g_pool.mu);
-        if (id < nsplit) copy_share(dst, src, bytes, nsplit, id);
-        g_pool.pending.fetch_sub(1, std::memory_order_release);
-        pthread_mutex_lock(&g_pool.mu);
-    }
-    return nullptr;
-}
-
-static void fast_copy(void *dst, const void *src, size_t bytes)
-{
-    if (!g_pool.started) {
-        g_pool.started = true;
-        const int want = std::max(1, std::min(16, env_int("B200_SPMV_COPY_THREADS", 4))) - 1;
-        for (int i = 0; i < want; ++i) {
-            pthread_t t;
-            if (pthread_create(&t, nullptr, copy_worker, (void *)(intptr_t)(i + 1)) != 0) break;
-            pthread_detach(t);
-            g_pool.nworkers++;
-        }
-    }
-    if (g_pool.nworkers == 0 || bytes < (256u << 10)) { memcpy(dst, src, bytes); return; }
-    pthread_mutex_lock(&g_pool.mu);
-    g_pool.dst = (char *)dst; g_pool.src = (const char *)src; g_pool.bytes = bytes;
-    g_pool.nsplit = g_pool.nworkers + 1;
-    g_pool.pending.store(g_pool.nworkers, std::memory_order_relaxed);
-    g_pool.generation++;
-    pthread_cond_broadcast(&g_pool.cv);
-    pthread_mutex_unlock(&g_pool.mu);
-    copy_share((char *)dst, (const char *)src, bytes, g_pool.nworkers + 1, 0);
-    while (g_pool.pending.load(std::memory_order_acquire) > 0) { }     /* tens of microseconds */
 }
 
 /* ------------------------------------------------------------------------
@@ -592,7 +527,7 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
             x_alias = (const char *)pinned_device_alias(iv, x_used);
             x_pinned = (const char *)iv;
             if (!x_alias) {
-                fast_copy(e.h_x, iv, x_used);
+                memcpy(e.h_x, iv, x_used);
                 x_pinned = (const char *)e.h_x;
                 x_alias = (const char *)pinned_device_alias(e.h_x, x_used);
                 if (!x_alias) die("the pinned bounce buffer has no device alias");
@@ -655,7 +590,7 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
                 kernel_ms = std::max(kernel_ms, ms);
             }
         }
-        if (!y_direct) fast_copy(ov, e.h_y, (size_t)n * es);
+        if (!y_direct) memcpy(ov, e.h_y, (size_t)n * es);
         g_stats.kernel_ms += kernel_ms;
         g_stats.kernel_launches += (uint64_t)launched;
         g_stats.h2d_bytes += x_used;

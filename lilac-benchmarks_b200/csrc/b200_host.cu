@@ -438,11 +438,21 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
      * power-law graph (profiles/r01_run11_sweep_sell.txt): 256-row tiles, two
      * rows per lane (longest with shortest), 2-pair chunks (72 registers, so
      * 7 CTAs of 128 threads per SM keep the L1TEX gather pipe full). */
-    int G = env_int("B200_SPMV_SELL_G", 2);
-    if (G != 1 && G != 2) G = 2;
-    int R = env_int("B200_SPMV_SELL_ROWS", 128 * G);
-    const int gran = 32 * G;
-    R = std::max(gran, std::min(256 * G, (R + gran - 1) / gran * gran));
+    const int fmt = env_int("B200_SPMV_SELL_FMT", 1) == 0 ? 0 : 1;
+    const double mean_len = (double)m->nnz / m->rows;
+    int G, R;
+    if (fmt == 1) {
+        /* SELLU (spmv_sellu.cu): 128 threads, G rows per lane so that a lane stream is ~100 entries */
+        G = env_int("B200_SPMV_SELL_G", 0);
+        if (G != 2 && G != 4 && G != 8 && G != 16) G = mean_len <= 8 ? 16 : mean_len <= 16 ? 8 : mean_len <= 48 ? 4 : 2;
+        R = sellu_threads() * G;
+    } else {
+        G = env_int("B200_SPMV_SELL_G", 2);
+        if (G != 1 && G != 2) G = 2;
+        R = env_int("B200_SPMV_SELL_ROWS", 128 * G);
+        const int gran = 32 * G;
+        R = std::max(gran, std::min(256 * G, (R + gran - 1) / gran * gran));
+    }
     const double mean = (double)m->nnz / m->rows;
     /* cap: rows above it leave the tiles for the nnz-split path.  A narrow
      * length distribution (NPB, crsmat: max <= 4 x mean) keeps every row in the
@@ -489,9 +499,23 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     CUDA_OK(cudaMalloc((void **)&d_seglen, nseg * sizeof(uint16_t)));
     CUDA_OK(cudaMemsetAsync(d_seglen, 0, nseg * sizeof(uint16_t), m->ctx->stream));
     launch_sell_rowlen(m->d_rowptr, m->rows, R, cap, d_seglen, m->ctx->stream);
-    CUDA_OK(cudaMalloc((void **)&m->d_meta, (size_t)nblk * Tn * sizeof(ushort4)));
-    CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
-    launch_panel_sort(d_seglen, nblk, R, G, 1, m->d_meta, d_cnt, m->ctx->stream);
+    size_t meta_bytes;
+    uint16_t *d_slotlen = nullptr;
+    if (fmt == 1) {
+        /* rowids [nblk][G][T] followed by slotlen [nblk][4][G] */
+        const size_t n_ids = (size_t)nblk * R, n_sl = (size_t)nblk * spb * G;
+        meta_bytes = (n_ids + n_sl) * sizeof(uint16_t);
+        CUDA_OK(cudaMalloc((void **)&m->d_meta, meta_bytes));
+        d_slotlen = reinterpret_cast<uint16_t *>(m->d_meta) + n_ids;
+        CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
+        launch_sellu_sort(d_seglen, nblk, R, G, reinterpret_cast<uint16_t *>(m->d_meta), d_slotlen, d_cnt,
+                          m->ctx->stream);
+    } else {
+        meta_bytes = (size_t)nblk * Tn * sizeof(ushort4);
+        CUDA_OK(cudaMalloc((void **)&m->d_meta, meta_bytes));
+        CUDA_OK(cudaMalloc((void **)&d_cnt, ((size_t)nslices + 1) * sizeof(int)));
+        launch_panel_sort(d_seglen, nblk, R, G, 1, m->d_meta, d_cnt, m->ctx->stream);
+    }
     CUDA_OK(cudaGetLastError());
     std::vector<int> cnt((size_t)nslices + 1);
     CUDA_OK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, m->ctx->stream));
@@ -513,7 +537,10 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     DevSell &sm = m->sell;
     sm.val = m->d_pval; sm.col = m->d_scol; sm.meta = m->d_meta; sm.slice_off = m->d_slice_off;
     sm.rows = m->rows; sm.R = R; sm.G = G; sm.nblk = nblk; sm.padded = run;
-    sm.U = env_int("B200_SPMV_SELL_U", 2);
+    sm.fmt = fmt;
+    sm.rowids = reinterpret_cast<const uint16_t *>(m->d_meta);
+    sm.slotlen = d_slotlen;
+    sm.U = env_int("B200_SPMV_SELL_U", fmt == 1 ? 8 : 2);
     sm.n_long = n_long;
     /* short single-chunk rows first: they run with 8 lanes per row */
     const int short_len = sell_short_chunk_entries();
@@ -538,7 +565,14 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
         CUDA_OK(cudaMalloc(&m->d_carry, (size_t)std::max(n_carry, 1) * es));
         sm.multi = m->d_multi; sm.multi_rows = m->d_multi_rows; sm.carry = m->d_carry;
     }
-    if (m->dtype == B200_F64)
+    if (fmt == 1) {
+        if (m->dtype == B200_F64)
+            launch_sellu_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm, cap,
+                                      (double *)m->d_pval, m->d_scol, m->ctx->stream);
+        else
+            launch_sellu_fill<float>((const float *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm, cap,
+                                     (float *)m->d_pval, m->d_scol, m->ctx->stream);
+    } else if (m->dtype == B200_F64)
         launch_sell_fill<double>((const double *)m->d_val, m->d_col, m->d_rowptr, m->rows, sm,
                                  d_seglen, (double *)m->d_pval, m->d_scol, m->ctx->stream);
     else
@@ -547,7 +581,7 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
     CUDA_OK(cudaFree(d_seglen));
-    m->resident_bytes = (int64_t)(nval * (es + 4) + (size_t)nblk * Tn * 8 + ((size_t)nslices + 1) * 4 +
+    m->resident_bytes = (int64_t)(nval * (es + 4) + meta_bytes + ((size_t)nslices + 1) * 4 +
                                   ((size_t)m->rows + 1) * 4);
     if (sm.n_chunks == 0) {
         CUDA_OK(cudaFree(m->d_val)); m->d_val = nullptr;

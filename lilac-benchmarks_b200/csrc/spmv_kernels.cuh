@@ -133,6 +133,10 @@ struct DevSell {
     const int     *slice_off;  /* int[nblk * R/G/32 + 1] element offsets (multiples of 64) */
     int rows, R, G, nblk, U;
     long long padded;
+    /* fmt 1 ("SELLU", spmv_sellu.cu): uniform row slots, entry-granular streams */
+    int fmt;                   /* 0: paired rows (spmv_sell.cu); 1: uniform slots (spmv_sellu.cu) */
+    const uint16_t *rowids;    /* fmt 1: [nblk][G][128] tile-local row of slot g of thread t */
+    const uint16_t *slotlen;   /* fmt 1: [nblk][4][G] entries of slot g in every lane of warp w */
     /* rows above the cap: nnz-split chunks + ordered carry fix-up (re-ordering) */
     const int4 *chunks;        /* {row, lo, hi, carry slot or -1} per chunk; short chunks first */
     int n_chunks;
@@ -147,6 +151,15 @@ void launch_sell_rowlen(const int *rowptr, int rows, int R, int cap, uint16_t *s
 template <typename T>
 void launch_sell_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm,
                       const uint16_t *seglen, T *val_out, int *col_out, cudaStream_t s);
+/* SELLU build passes and product (spmv_sellu.cu); the long-row path stays launch_sell's */
+int sellu_threads();
+void launch_sellu_sort(const uint16_t *seglen, int ntiles, int R, int G, uint16_t *rowids,
+                       uint16_t *slotlen, int *slice_elems, cudaStream_t s);
+template <typename T>
+void launch_sellu_fill(const T *val, const int *col, const int *rowptr, int rows, const DevSell &sm, int cap,
+                       T *val_out, int *col_out, cudaStream_t s);
+template <typename T>
+void launch_sellu(const DevSell &sm, const T *x, T *y, cudaStream_t s);
 int sell_chunk_entries();
 int sell_short_chunk_entries();
 template <typename T>

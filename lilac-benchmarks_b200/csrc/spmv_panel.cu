@@ -406,7 +406,11 @@ void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
     const int threads = pm.R / pm.G;
-    if (threads <= 256 && pm.U >= 5) {
+    if (threads <= 128 && pm.U >= 12) {
+        /* a handful of warps per SM (NPB class A and smaller: one row per lane, ~100 rows
+         * per SM): latency-bound, so each lane keeps 24 pairs of its stream in flight */
+        launch_panel_cfg<T, 12, 128>(pm, x, y, s);
+    } else if (threads <= 256 && pm.U >= 5) {
         /* few warps per SM (NPB class A / B sized row blocks): the register file
          * is free, so each lane keeps twice as many pairs of the stream in flight */
         if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, s);

@@ -290,7 +290,9 @@ static void launch_sell_u(const DevSell &sm, const T *x, T *y, cudaStream_t s)
 template <typename T>
 void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStream_t s)
 {
-    if (sm.nblk > 0) {
+    if (sm.nblk > 0 && sm.fmt == 1) {
+        launch_sellu<T>(sm, x, y, s);
+    } else if (sm.nblk > 0) {
         if (sm.U >= 6) launch_sell_u<T, 6>(sm, x, y, s);
         else if (sm.U <= 2) launch_sell_u<T, 2>(sm, x, y, s);
         else launch_sell_u<T, 4>(sm, x, y, s);

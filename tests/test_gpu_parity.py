@@ -186,8 +186,10 @@ def test_panel_falls_back_when_rows_are_unsorted(libspmv, oracle):
     dict(n=1, ncols=1, mean=1), dict(n=65, ncols=9, mean=3), dict(n=5000, ncols=300000, mean=5),
     dict(n=3000, ncols=1500000, mean=120), dict(n=777, ncols=50000, mean=400),
 ])
-@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SELL_G": 1, "B200_SPMV_SELL_ROWS": 64},
-                                 {"B200_SPMV_SELL_U": 2}, {"B200_SPMV_SELL_U": 6}])
+@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SELL_G": 2}, {"B200_SPMV_SELL_G": 16, "B200_SPMV_SELL_U": 4},
+                                 {"B200_SPMV_SELL_U": 6}, {"B200_SPMV_SELL_G": 8, "B200_SPMV_SELL_U": 8},
+                                 {"B200_SPMV_SELL_FMT": 0}, {"B200_SPMV_SELL_FMT": 0, "B200_SPMV_SELL_U": 6},
+                                 {"B200_SPMV_SELL_FMT": 0, "B200_SPMV_SELL_G": 1, "B200_SPMV_SELL_ROWS": 64}])
 def test_sell_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape, env):
     """Lane streams over L2 gathers: left-to-right rows whatever the column
     order, for every row up to the cap."""
