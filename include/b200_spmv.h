@@ -102,6 +102,18 @@ int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y, void *stre
                           const unsigned long long *flags, unsigned long long epoch,
                           int cols_per_rank, int nranks);
 
+/* The exchange fused into the product (include/b200_peer.h): the kernel first stores this
+ * rank's slice v_local[0..n_local) -- element offset `lo` of the full vector -- into every
+ * rank's buffer of `epoch` over NVLink peer memory and publishes the epoch, then runs the
+ * product on the local buffer, waiting per slice.  One launch per sharded step.  Returns -1
+ * without launching when the kernel family or the grid cannot do that (more row blocks
+ * than SMs, odd slice boundaries): use b200_peer_post + b200_spmv_exec_sliced then. */
+int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, void *peer_group,
+                          const double *v_local, int n_local, int64_t lo, uint64_t epoch,
+                          int cols_per_rank);
+
+int b200_spmv_can_push(const b200_matrix *m);    /* 1: b200_spmv_exec_pushed works for this matrix */
+
 /* Upload from DEVICE arrays of the current device (same 1-based contents as the ABI;
  * the on-device NPB generator produces them): no PCIe traffic. */
 b200_matrix *b200_spmv_upload_device(const void *d_a, const int *d_rowstr, const int *d_colidx,

@@ -253,13 +253,16 @@ static bool panel_plan_beats_sell(const b200_matrix *m, const PanelPlan &pl)
     return t_panel < 0.92 * t_sell;
 }
 
-static bool panel_applicable(const b200_matrix *m, int *P_out, int *W_out, int *R_out, int *G_out,
-                             int *nbuf_out)
+static bool panel_applicable(const b200_matrix *m, int g_default, int *P_out, int *W_out, int *R_out,
+                             int *G_out, int *nbuf_out)
 {
     if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
     if (m->scan.rows_unsorted != 0) return false;
     const size_t es = elem_size(m->dtype);
-    int G = env_int("B200_SPMV_PANEL_G", 2);
+    /* g_default: two rows per lane (longest with shortest), or one row per lane when there are
+     * so few rows that every lane counts (NPB class A: 95 rows per SM; 16.5 us against 18.5 us,
+     * profiles/r02_run1_sweep.txt) */
+    int G = env_int("B200_SPMV_PANEL_G", g_default);
     G = G == 1 ? 1 : 2;
     int R = env_int("B200_SPMV_PANEL_ROWS", 0);
     if (R <= 0) R = (m->rows + m->ctx->sm_count - 1) / m->ctx->sm_count;
@@ -309,7 +312,10 @@ static bool build_panel_locked(b200_matrix *m, bool forced)
     int P, W, R, G, nbuf, fmt = 0, ring_K = 0, ring_S = 0;
     const int want_fmt = env_int("B200_SPMV_PANEL_FMT", -1);
     bool ok = false;
-    if (want_fmt <= 0 && panel_applicable(m, &P, &W, &R, &G, &nbuf)) {
+    /* one row per lane first when rows are scarce (see panel_applicable), else two */
+    const int g_first = m->rows <= 128 * m->ctx->sm_count ? 1 : 2;
+    for (int g_try = g_first; g_try <= 2 && !ok && want_fmt <= 0; ++g_try) {
+        if (!panel_applicable(m, g_try, &P, &W, &R, &G, &nbuf)) continue;
         /* every CTA loads the whole x once: only worth it while that stays below the
          * matrix stream itself (short, wide row blocks fail this: NPB class D shards) */
         const double x_bytes = (double)((m->rows + R - 1) / R) * (double)P * W * elem_size(m->dtype);
@@ -438,13 +444,17 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
      * power-law graph (profiles/r01_run11_sweep_sell.txt): 256-row tiles, two
      * rows per lane (longest with shortest), 2-pair chunks (72 registers, so
      * 7 CTAs of 128 threads per SM keep the L1TEX gather pipe full). */
-    const int fmt = env_int("B200_SPMV_SELL_FMT", 1) == 0 ? 0 : 1;
     const double mean_len = (double)m->nnz / m->rows;
+    /* short rows: uniform row slots (spmv_sellu.cu); long rows (NPB class D / E blocks): paired
+     * rows with 128-bit loads (spmv_sell.cu).  Measured, kernel only (profiles/r02_run6_sweep.txt):
+     * crsmat170 127 -> 120 us, power-law 2^22 370 -> 324 us, class D 1/8 block 383 us paired
+     * against 412-558 us with slots. */
+    const int fmt = env_int("B200_SPMV_SELL_FMT", mean_len <= 64.0 ? 1 : 0) == 0 ? 0 : 1;
     int G, R;
     if (fmt == 1) {
-        /* SELLU (spmv_sellu.cu): 128 threads, G rows per lane so that a lane stream is ~100 entries */
+        /* 128 threads, G rows per lane; small tiles keep the grid many waves deep */
         G = env_int("B200_SPMV_SELL_G", 0);
-        if (G != 2 && G != 4 && G != 8 && G != 16) G = mean_len <= 8 ? 16 : mean_len <= 16 ? 8 : mean_len <= 48 ? 4 : 2;
+        if (G != 2 && G != 4 && G != 8 && G != 16) G = mean_len <= 8 ? 4 : mean_len <= 24 ? 8 : 4;
         R = sellu_threads() * G;
     } else {
         G = env_int("B200_SPMV_SELL_G", 2);
@@ -540,7 +550,7 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     sm.fmt = fmt;
     sm.rowids = reinterpret_cast<const uint16_t *>(m->d_meta);
     sm.slotlen = d_slotlen;
-    sm.U = env_int("B200_SPMV_SELL_U", fmt == 1 ? 8 : 2);
+    sm.U = env_int("B200_SPMV_SELL_U", fmt == 1 ? 4 : 2);
     sm.n_long = n_long;
     /* short single-chunk rows first: they run with 8 lanes per row */
     const int short_len = sell_short_chunk_entries();
@@ -736,7 +746,8 @@ bool exec_waits_in_kernel(const b200_matrix *m)
     return m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 2;
 }
 
-int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf)
+int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
+                const XPush *xp)
 {
     if (m->rows == 0) return 0;
     int launched_kernels = 1;
@@ -744,10 +755,13 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
         if (m->panel.fmt == 2) {
             XFlags xf = {nullptr, 0ull, 1, 0};
             if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks; }
+            XPush none;
+            none.src = nullptr;
+            const XPush &push = xp ? *xp : none;
             if (m->dtype == B200_F64)
-                launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, xf, s);
+                launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, xf, push, s);
             else
-                launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, s);
+                launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, push, s);
         } else if (m->dtype == B200_F64)
             launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
         else
@@ -841,6 +855,36 @@ extern "C" int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y,
     DeviceScope scope(m->device);
     SliceFlags sf = {flags, epoch, cols_per_rank, nranks};
     return exec_locked(m, d_x, d_y, (cudaStream_t)stream, &sf);
+}
+
+/* defined in cg_peer.cu: the pointers and flags of a peer group for one push */
+struct b200_peer_group;
+extern "C" int b200_peer_describe_push(b200_peer_group *g, const double *v, int n_local, int64_t lo,
+                                       uint64_t e, b200::XPush *out, const double **xbuf,
+                                       const unsigned long long **vflags, int *cols_per_rank);
+
+extern "C" int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, void *peer_group,
+                                     const double *v_local, int n_local, int64_t lo, uint64_t epoch,
+                                     int cols_per_rank)
+{
+    if (!m || !peer_group) die("b200_spmv_exec_pushed: null argument");
+    /* the publishing CTA waits for all others: they must be co-resident (one per SM) */
+    if (!exec_waits_in_kernel(m) || m->dtype != B200_F64 || m->panel.nblk > m->ctx->sm_count) return -1;
+    XPush xp;
+    const double *xbuf = nullptr;
+    const unsigned long long *vflags = nullptr;
+    int cpr = 0;
+    if (b200_peer_describe_push((b200_peer_group *)peer_group, v_local, n_local, lo, epoch, &xp, &xbuf,
+                                &vflags, &cpr) != 0)
+        return -1;
+    DeviceScope scope(m->device);
+    SliceFlags sf = {vflags, epoch, cols_per_rank, xp.nranks};
+    return exec_locked(m, xbuf, d_y, (cudaStream_t)stream, &sf, &xp);
+}
+
+extern "C" int b200_spmv_can_push(const b200_matrix *m)
+{
+    return exec_waits_in_kernel(m) && m->dtype == B200_F64 && m->panel.nblk <= m->ctx->sm_count ? 1 : 0;
 }
 
 extern "C" int b200_spmv_device(const b200_matrix *m) { return m->device; }

@@ -11,6 +11,7 @@
  * never waits on work queued behind it on its own device.
  */
 #include "../../include/b200_peer.h"
+#include "spmv_kernels.cuh"
 
 #include <cuda_runtime.h>
 
@@ -137,6 +138,27 @@ __device__ __forceinline__ void publish_scalar(const PeerDev &g, int slot, unsig
     }
 }
 
+/* dst[j][lo + 2 i .. 2 i + 1] = v2[i] for every rank j, grid-stride: the loads of four
+ * elements are issued before their stores, so a thread pays the load latency once per four
+ * elements, not once per element (a load-store-load-store loop serialises: the compiler must
+ * assume the peer buffers alias the source) */
+__device__ __forceinline__ void push_slice_vec(const double2 *__restrict__ v2, int n2, double *const *dst,
+                                               long long lo, int nranks)
+{
+    const int stride = gridDim.x * kThreads;
+    for (int base = blockIdx.x * kThreads + threadIdx.x; base < n2; base += 4 * stride) {
+        double2 val[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (base + q * stride < n2) val[q] = v2[base + q * stride];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (base + q * stride < n2)
+                for (int j = 0; j < nranks; ++j)
+                    reinterpret_cast<double2 *>(dst[j] + lo)[base + q * stride] = val[q];
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, unsigned long long e,
                  unsigned long long e_consumed)
@@ -147,11 +169,7 @@ peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
     const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
     const int n2 = vec_ok ? n >> 1 : 0;
     const double2 *v2 = reinterpret_cast<const double2 *>(v);
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
-        const double2 val = v2[i];
-        for (int j = 0; j < g.nranks; ++j)
-            reinterpret_cast<double2 *>(g.xfull[j] + lo)[i] = val;
-    }
+    push_slice_vec(v2, n2, g.xfull, lo, g.nranks);
     for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
@@ -178,11 +196,7 @@ peer_exchange_kernel(PeerDev g, const double *__restrict__ v, int n, long long l
     const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
     const int n2 = vec_ok ? n >> 1 : 0;
     const double2 *v2 = reinterpret_cast<const double2 *>(v);
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
-        const double2 val = v2[i];
-        for (int j = 0; j < g.nranks; ++j)
-            reinterpret_cast<double2 *>(g.xfull[j] + lo)[i] = val;
-    }
+    push_slice_vec(v2, n2, g.xfull, lo, g.nranks);
     for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
@@ -211,11 +225,8 @@ peer_post_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
     const bool vec_ok = ((lo & 1) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
     const int n2 = vec_ok ? n >> 1 : 0;
     const double2 *v2 = reinterpret_cast<const double2 *>(v);
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n2; i += gridDim.x * kThreads) {
-        const double2 val = v2[i];
-        for (int j = 0; j < g.nranks; ++j)
-            reinterpret_cast<double2 *>(dstv[j] + lo)[i] = val;
-    }
+    /* four loads in flight per thread before the stores (see push_slice_vec) */
+    push_slice_vec(v2, n2, dstv, lo, g.nranks);
     for (int i = 2 * n2 + blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) dstv[j][lo + i] = val;
@@ -416,6 +427,32 @@ extern "C" double *b200_peer_xbuf(b200_peer_group *g, uint64_t e)
 }
 
 extern "C" const unsigned long long *b200_peer_vflags(b200_peer_group *g) { return g->dev.vflag[g->rank]; }
+
+/* what a product kernel needs to do the push of epoch e itself (b200_spmv_exec_pushed) */
+extern "C" int b200_peer_describe_push(b200_peer_group *g, const double *v, int n_local, int64_t lo,
+                                       uint64_t e, b200::XPush *out, const double **xbuf,
+                                       const unsigned long long **vflags, int *cols_per_rank)
+{
+    if (!g || !g->connected) return -1;
+    /* 16-byte granules on both sides */
+    if ((lo & 1) || (n_local & 1) || (reinterpret_cast<uintptr_t>(v) & 15)) return -1;
+    out->src = v;
+    out->bytes = (size_t)n_local * sizeof(double);
+    out->offset = (size_t)lo * sizeof(double);
+    out->rank = g->rank;
+    out->nranks = g->nranks;
+    out->epoch = e;
+    for (int j = 0; j < g->nranks; ++j) {
+        out->dst[j] = (e & 1) ? (void *)g->dev.xalt[j] : (void *)g->dev.xfull[j];
+        out->vflag[j] = g->dev.vflag[j];
+        out->rflag[j] = g->dev.rflag[j];
+    }
+    out->counter = g->counter + 5;
+    *xbuf = (e & 1) ? g->dev.xalt[g->rank] : g->dev.xfull[g->rank];
+    *vflags = g->dev.vflag[g->rank];
+    if (cols_per_rank) *cols_per_rank = 0;
+    return 0;
+}
 
 extern "C" void b200_peer_post(b200_peer_group *g, const double *v, int n_local, int64_t lo, uint64_t e,
                                void *stream)

@@ -105,7 +105,8 @@ void release_locked(b200_matrix *m);
 /* launches on `s` (a stream of m->device, which must be current); returns the number of
  * kernels launched.  `sf` != NULL: the kernel itself waits for the x slices (only the
  * RING kernel can; for the others the caller must have waited -- see exec_waits_in_kernel) */
-int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf);
+int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
+                const XPush *xp = nullptr);
 bool exec_waits_in_kernel(const b200_matrix *m);
 
 }  // namespace b200

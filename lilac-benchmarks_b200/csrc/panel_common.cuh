@@ -62,6 +62,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     return v;
 }
 
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 /* host side: true when the calling device has been seen before (bit per device ordinal);
  * used to set function attributes once per device (callers hold the library lock, or
  * race benignly: setting an attribute twice is harmless) */

@@ -115,10 +115,26 @@ struct XFlags {
     int cols_per_rank;
     int nranks;
 };
+/* The exchange fused into the product: the kernel's CTAs first store this rank's slice into
+ * every rank's buffer of the epoch (NVLink peer stores), the last one publishes the epoch;
+ * then they walk the panels, waiting per slice (XFlags).  src == NULL: no push.
+ * Only for grids whose CTAs are all co-resident (nblk <= SM count): the publishing CTA
+ * waits for the others. */
+struct XPush {
+    const void *src;                    /* local slice */
+    size_t bytes;                       /* its size, and */
+    size_t offset;                      /* its byte offset inside the full vector */
+    int rank, nranks;
+    unsigned long long epoch;
+    void *dst[8];                       /* every rank's full-length buffer of this epoch */
+    unsigned long long *vflag[8];       /* every rank's row of vector flags */
+    unsigned long long *rflag[8];       /* every rank's row of consumed flags */
+    unsigned int *counter;              /* local arrival counter (zero between launches) */
+};
 /* ... and its kernel: the matrix stream through per-warp shared-memory rings (spmv_panelr.cu);
  * waits per x slice on `xf` before it requests the panels that need the slice */
 template <typename T>
-void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s);
+void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, const XPush &xp, cudaStream_t s);
 size_t panelr_smem_bytes(const DevPanel &pm, bool f32);
 
 /* ------------------------------------------------------------------------

@@ -99,6 +99,9 @@ __device__ __forceinline__ void consume_rows(const unsigned char *rows, int lane
 #ifndef B200_RING_WAR_FENCE
 #define B200_RING_WAR_FENCE 0
 #endif
+#ifndef B200_RING_TAILS
+#define B200_RING_TAILS 0      /* size-specialised tail batches: measured 1 % slower, see below */
+#endif
 #ifndef B200_XCOPY_BYTES
 #define B200_XCOPY_BYTES 262144
 #endif
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 spmv_panelr_kernel(const unsigned char *__restrict__ stream,
                    const uint16_t *__restrict__ rowids, const int *__restrict__ slice_off,
                    const T *__restrict__ x, T *__restrict__ y,
-                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S, XFlags xf)
+                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf, int S, XFlags xf, XPush xp)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -159,6 +162,54 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
     };
     if (lane == 0)
         for (int t = 0; t < S && t < nstage; ++t) issue_stage(t, t);
+
+    /* The exchange, fused: with the first stages of the matrix stream requested, every CTA
+     * stores its share of this rank's x slice into all ranks' buffers.  Epoch e goes to the
+     * buffer the products of epoch e - 2 read last: report e - 1 as consumed (the product
+     * that read it precedes this kernel in the stream), wait for everybody's report of e - 2. */
+    if (xp.src) {
+        if (blockIdx.x == 0 && tid == 0 && xp.epoch > 1) {
+            __threadfence_system();
+            for (int j = 0; j < xp.nranks; ++j) st_release_sys_u64(xp.rflag[j] + xp.rank, xp.epoch - 1);
+        }
+        if (xp.epoch > 2) {
+            if (tid < xp.nranks)
+                while (ld_acquire_sys_u64(xp.rflag[xp.rank] + tid) < xp.epoch - 2) { }
+            __syncthreads();
+        }
+        const size_t n16 = xp.bytes >> 4;                     /* slices are 16-byte granular */
+        const size_t per = (n16 + gridDim.x - 1) / gridDim.x;
+        const size_t i0 = min(n16, per * blockIdx.x), i1 = min(n16, i0 + per);
+        const int4 *src = reinterpret_cast<const int4 *>(xp.src);
+        /* four loads in flight per thread, then the stores: a load-store-load-store loop would
+         * pay the load latency once per element (source and destinations may alias for all
+         * the compiler knows) */
+        for (size_t base = i0; base < i1; base += (size_t)Tn * 4) {
+            int4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const size_t i = base + (size_t)q * Tn + tid;
+                if (i < i1) v[q] = __ldg(src + i);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const size_t i = base + (size_t)q * Tn + tid;
+                if (i < i1)
+                    for (int j = 0; j < xp.nranks; ++j)
+                        reinterpret_cast<int4 *>(static_cast<char *>(xp.dst[j]) + xp.offset)[i] = v[q];
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(xp.counter, 1u);
+            if (prev == gridDim.x - 1) {                      /* everybody's stores are out */
+                *xp.counter = 0;
+                __threadfence_system();
+                for (int j = 0; j < xp.nranks; ++j) st_release_sys_u64(xp.vflag[j] + xp.rank, xp.epoch);
+            }
+        }
+    }
 
     /* x assembled from the slices of several GPUs: the slices a panel needs must have
      * arrived (epoch flag written with st.release.sys by the pushing rank after its stores)
@@ -225,7 +276,11 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
 
     for (int p = 0; p < P; ++p) {
         /* first thing after the barrier: request the x slice (thread 0's warp is on
-         * everybody's critical path, so nothing is queued in front of the request) */
+         * everybody's critical path, so nothing is queued in front of the request).
+         * CTAs are deliberately NOT kept in step with each other: a soft grid barrier every
+         * n panels (all CTAs are co-resident) made the class D 1/8 block slower the more
+         * often it ran -- 275 us without, 295 us every 16 panels, 391 us every panel
+         * (profiles/r02_run7_sweep.txt); staggered slice requests suit the L2 better. */
         if (use_tma && tid == 0) {
             if (nbuf == 2 && p + 1 < P) issue_panel(p + 1);
             if (nbuf == 1 && p > 0) issue_panel(p);
@@ -260,10 +315,21 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
             if (n == K) {
                 consume_rows<T, G, K, true>(rows_at, lane, n, xs, sums, st);
             } else {
-                /* head / tail of a panel inside a stage: one pair row at a time (lean code
-                 * beats a predicated unrolled batch here) */
-                for (int u = 0; u < n; ++u)
-                    consume_rows<T, G, 1, true>(rows_at + u * kRowB, lane, 1, xs, sums, st);
+                /* head / tail of a panel inside a stage: one pair row at a time.  Lean code wins
+                 * here: a predicated K-batch was slower, and so were batches specialised on
+                 * their size (B200_RING_TAILS=1: class D 1/8 block 274.8 us against 273.2 us,
+                 * 1/2 block 853 us against 842 us, profiles/r02_run8_sweep*.txt) */
+#if B200_RING_TAILS
+                if (K >= 4 && n == 3) {
+                    consume_rows<T, G, 3, true>(rows_at, lane, 3, xs, sums, st);
+                } else if (n == 2) {
+                    consume_rows<T, G, 2, true>(rows_at, lane, 2, xs, sums, st);
+                } else
+#endif
+                {
+                    for (int u = 0; u < n; ++u)
+                        consume_rows<T, G, 1, true>(rows_at + u * kRowB, lane, 1, xs, sums, st);
+                }
             }
             kp += n;
             sr += n;
@@ -313,7 +379,7 @@ size_t panelr_smem_bytes(const DevPanel &pm, bool f32)
 }
 
 template <typename T, int G, int K, int MAXT>
-static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
+static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, const XFlags &xf, const XPush &xp, cudaStream_t s)
 {
     static unsigned attr_set = 0;                  /* function attributes are per device */
     if (!attr_done(&attr_set))
@@ -323,31 +389,31 @@ static void launch_panelr_cfg(const DevPanel &pm, const T *x, T *y, const XFlags
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panelr_kernel<T, G, K, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const unsigned char *>(pm.val), pm.rowids, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S, xf);
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, pm.ring_S, xf, xp);
 }
 
 template <typename T, int G>
-static void launch_panelr_g(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
+static void launch_panelr_g(const DevPanel &pm, const T *x, T *y, const XFlags &xf, const XPush &xp, cudaStream_t s)
 {
     const int threads = pm.R / pm.G;
     if (threads > 512) {
-        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 768>(pm, x, y, xf, s);
-        else                launch_panelr_cfg<T, G, 4, 768>(pm, x, y, xf, s);
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 768>(pm, x, y, xf, xp, s);
+        else                launch_panelr_cfg<T, G, 4, 768>(pm, x, y, xf, xp, s);
     } else {
-        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 512>(pm, x, y, xf, s);
-        else                launch_panelr_cfg<T, G, 4, 512>(pm, x, y, xf, s);
+        if (pm.ring_K == 2) launch_panelr_cfg<T, G, 2, 512>(pm, x, y, xf, xp, s);
+        else                launch_panelr_cfg<T, G, 4, 512>(pm, x, y, xf, xp, s);
     }
 }
 
 template <typename T>
-void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, cudaStream_t s)
+void launch_panelr(const DevPanel &pm, const T *x, T *y, const XFlags &xf, const XPush &xp, cudaStream_t s)
 {
     if (pm.nblk <= 0) return;
-    if (pm.G == 2)      launch_panelr_g<T, 2>(pm, x, y, xf, s);
-    else if (pm.G == 4) launch_panelr_g<T, 4>(pm, x, y, xf, s);
-    else                launch_panelr_g<T, 8>(pm, x, y, xf, s);
+    if (pm.G == 2)      launch_panelr_g<T, 2>(pm, x, y, xf, xp, s);
+    else if (pm.G == 4) launch_panelr_g<T, 4>(pm, x, y, xf, xp, s);
+    else                launch_panelr_g<T, 8>(pm, x, y, xf, xp, s);
 }
-template void launch_panelr<double>(const DevPanel &, const double *, double *, const XFlags &, cudaStream_t);
-template void launch_panelr<float>(const DevPanel &, const float *, float *, const XFlags &, cudaStream_t);
+template void launch_panelr<double>(const DevPanel &, const double *, double *, const XFlags &, const XPush &, cudaStream_t);
+template void launch_panelr<float>(const DevPanel &, const float *, float *, const XFlags &, const XPush &, cudaStream_t);
 
 }  // namespace b200

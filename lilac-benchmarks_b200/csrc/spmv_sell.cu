@@ -263,18 +263,27 @@ spmv_long_chunks_kernel(const T *__restrict__ val, const int *__restrict__ col,
     }
 }
 
-/* one thread per multi-chunk row: y[row] = carry[first] + carry[first+1] + ... */
+/* one warp per multi-chunk row: y[row] = carry[first] + carry[first+1] + ... in chunk order.
+ * The lanes fetch 32 carries at a time (one coalesced load instead of a chain of dependent
+ * ones: a 65536-entry row has 128 chunks) and the sum walks them in order through shuffles,
+ * so the result does not depend on the lane count: same bits as a single thread adding. */
 template <typename T>
-__global__ void spmv_long_fixup_kernel(const int2 *__restrict__ multi, int n_multi,
-                                       const int *__restrict__ rows, const T *__restrict__ carry,
-                                       T *__restrict__ y)
+__global__ void __launch_bounds__(256)
+spmv_long_fixup_kernel(const int2 *__restrict__ multi, int n_multi,
+                       const int *__restrict__ rows, const T *__restrict__ carry,
+                       T *__restrict__ y)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_multi) return;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= n_multi) return;                  /* whole warps leave together */
     const int2 m = multi[t];                   /* {first carry slot, count} */
     T acc = (T)0;
-    for (int k = 0; k < m.y; ++k) acc = sadd(acc, carry[m.x + k]);
-    y[rows[t]] = acc;
+    for (int k0 = 0; k0 < m.y; k0 += 32) {
+        const int n = min(32, m.y - k0);
+        const T v = lane < n ? carry[m.x + k0 + lane] : (T)0;
+        for (int k = 0; k < n; ++k) acc = sadd(acc, __shfl_sync(0xffffffffu, v, k));
+    }
+    if (lane == 0) y[rows[t]] = acc;
 }
 
 int sell_chunk_entries() { return kChunk; }
@@ -307,7 +316,7 @@ void launch_sell(const DevSell &sm, const DevCsr &csr, const T *x, T *y, cudaStr
             static_cast<const T *>(csr.val), csr.col, sm.chunks + sm.n_chunks_short,
             sm.n_chunks - sm.n_chunks_short, x - 1, y, static_cast<T *>(sm.carry));
     if (sm.n_multi > 0)
-        spmv_long_fixup_kernel<T><<<(sm.n_multi + 255) / 256, 256, 0, s>>>(
+        spmv_long_fixup_kernel<T><<<(sm.n_multi + 7) / 8, 256, 0, s>>>(
             sm.multi, sm.n_multi, sm.multi_rows, static_cast<const T *>(sm.carry), y);
 }
 template void launch_sell<double>(const DevSell &, const DevCsr &, const double *, double *, cudaStream_t);

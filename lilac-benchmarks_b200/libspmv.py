@@ -66,6 +66,11 @@ def lib():
     L.b200_spmv_exec_sliced.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64,
                                         c_int, c_int]
     L.b200_spmv_exec_sliced.restype = c_int
+    L.b200_spmv_exec_pushed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                        c_uint64, c_int]
+    L.b200_spmv_exec_pushed.restype = c_int
+    L.b200_spmv_can_push.argtypes = [c_void_p]
+    L.b200_spmv_can_push.restype = c_int
     L.b200_spmv_upload_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
     L.b200_spmv_upload_device.restype = c_void_p
     L.b200_spmv_device.argtypes = [c_void_p]
@@ -269,6 +274,7 @@ class ResidentMatrix:
         self.resident_bytes = L.b200_spmv_resident_bytes(self._h)
         self.device = L.b200_spmv_device(self._h)
         self.waits_in_kernel = bool(L.b200_spmv_waits_in_kernel(self._h))
+        self.can_push = bool(L.b200_spmv_can_push(self._h))
 
     def exec_sliced_ptr(self, d_x, d_y, stream, flags, epoch, cols_per_rank, nranks):
         """Product on an x that is still arriving slice by slice (include/b200_peer.h);

@@ -355,11 +355,13 @@ class PeerShardedSpmv:
     rank's previous product) and publishes the epoch; the product then waits per slice,
     just before the column panels that need it (`b200_spmv_exec_sliced`), i.e. it starts
     on the slices that have arrived while the others are still in flight.
+    Fused form (row blocks of at most one CTA per SM): the product kernel does the push
+    itself in its prologue (`b200_spmv_exec_pushed`) -- one launch per step.
     Other kernels: one exchange kernel that also waits for every rank's slice, then the
     product."""
 
     def __init__(self, libspmv_module, resident_matrix, layout, rank, dist=None, device="cuda",
-                 overlap=True):
+                 overlap=True, fused=True):
         import ctypes as C
         import torch
         self.torch = torch
@@ -391,12 +393,27 @@ class PeerShardedSpmv:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             ok = int(t.item())
         self.overlap = bool(ok)
+        # fused form: the product kernel pushes the slice itself (one launch per step); needs
+        # every rank's row blocks co-resident (one CTA per SM) and 16-byte slice boundaries
+        okf = 1 if (self.overlap and fused and resident_matrix.can_push and
+                    all(int(b) % 2 == 0 for b in layout.bounds)) else 0
+        if dist is not None and world > 1:
+            t = torch.tensor([okf], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            okf = int(t.item())
+        self.fused = bool(okf)
 
     def step(self, x_local):
         s = self.torch.cuda.current_stream().cuda_stream
         self.epoch += 1
         e = self.epoch
-        if self.overlap:
+        if self.fused:
+            rc = self.L.b200_spmv_exec_pushed(self.rm._h, self.y_local.data_ptr(), s, self.g,
+                                              x_local.data_ptr(), self.hi - self.lo, self.lo, e,
+                                              self.layout.slot)
+            if rc < 0:
+                raise RuntimeError("b200_spmv_exec_pushed refused a matrix that reported can_push")
+        elif self.overlap:
             self.L.b200_peer_post(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, e, s)
             self.rm.exec_sliced_ptr(self.L.b200_peer_xbuf(self.g, e), self.y_local.data_ptr(), s,
                                     self.vflags, e, self.layout.slot, self.layout.parts)

@@ -44,8 +44,9 @@ def timed(fn, iters=50, warm=5):
 
 s = torch.cuda.current_stream().cuda_stream
 print(f"product alone           {timed(lambda i: rm.exec(x_local, y)):8.1f} us")
-for overlap in (True, False):
-    sh = sharded.PeerShardedSpmv(libspmv, rm, layout, 0, overlap=overlap)
+for overlap, fused in ((True, True), (True, False), (False, False)):
+    sh = sharded.PeerShardedSpmv(libspmv, rm, layout, 0, overlap=overlap, fused=fused)
+    print("fused", sh.fused)
     sh.y_local = y
     state = {"e": 0}
 

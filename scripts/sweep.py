@@ -59,7 +59,7 @@ for cfg_full in configs:
         kernel = "sell"
         for kv in cfg[5:].split(";"):
             k, v = kv.split("=")
-            env["B200_SPMV_SELL_" + {"R": "ROWS", "G": "G", "U": "U", "C": "CAP"}[k]] = v
+            env["B200_SPMV_SELL_" + {"R": "ROWS", "G": "G", "U": "U", "C": "CAP", "F": "FMT"}[k]] = v
     elif cfg.startswith("pr"):
         # ring panel for wide matrices: "pr:R=1280;G=4;W=12288;B=2;K=4;S=2"
         kernel = "panel"

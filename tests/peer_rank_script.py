@@ -39,9 +39,10 @@ def main():
     rng = np.random.default_rng(77)          # same stream on every rank
     xs = [rng.standard_normal(whole.n) for _ in range(5)]
     refs = [oracle.spmv(whole.a, x, whole.rowstr, whole.colidx, omp=True)[lo:hi] for x in xs]
-    for overlap in (True, False):
-        sh = sharded.PeerShardedSpmv(libspmv, rm, layout, rank, dist=dist, device=dev, overlap=overlap)
-        assert sh.overlap == overlap
+    for overlap, fused in ((True, True), (True, False), (False, False)):
+        sh = sharded.PeerShardedSpmv(libspmv, rm, layout, rank, dist=dist, device=dev, overlap=overlap,
+                                     fused=fused)
+        assert sh.overlap == overlap and sh.fused == (fused and rm.can_push), (sh.overlap, sh.fused)
         try:
             for it in range(3):                   # several sweeps: buffers and epochs get reused
                 for x, ref in zip(xs, refs):

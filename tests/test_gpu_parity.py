@@ -186,8 +186,10 @@ def test_panel_falls_back_when_rows_are_unsorted(libspmv, oracle):
     dict(n=1, ncols=1, mean=1), dict(n=65, ncols=9, mean=3), dict(n=5000, ncols=300000, mean=5),
     dict(n=3000, ncols=1500000, mean=120), dict(n=777, ncols=50000, mean=400),
 ])
-@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SELL_G": 2}, {"B200_SPMV_SELL_G": 16, "B200_SPMV_SELL_U": 4},
-                                 {"B200_SPMV_SELL_U": 6}, {"B200_SPMV_SELL_G": 8, "B200_SPMV_SELL_U": 8},
+@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SELL_FMT": 1}, {"B200_SPMV_SELL_FMT": 1, "B200_SPMV_SELL_G": 2},
+                                 {"B200_SPMV_SELL_FMT": 1, "B200_SPMV_SELL_G": 16, "B200_SPMV_SELL_U": 4},
+                                 {"B200_SPMV_SELL_FMT": 1, "B200_SPMV_SELL_U": 6},
+                                 {"B200_SPMV_SELL_FMT": 1, "B200_SPMV_SELL_G": 8, "B200_SPMV_SELL_U": 8},
                                  {"B200_SPMV_SELL_FMT": 0}, {"B200_SPMV_SELL_FMT": 0, "B200_SPMV_SELL_U": 6},
                                  {"B200_SPMV_SELL_FMT": 0, "B200_SPMV_SELL_G": 1, "B200_SPMV_SELL_ROWS": 64}])
 def test_sell_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape, env):
@@ -685,3 +687,60 @@ def test_device_makea_bit_identical_to_the_host_generator(libspmv, oracle, npb, 
         assert np.array_equal(dy.cpu().numpy(), oracle.spmv(ref.a, x, ref.rowstr, ref.colidx))
         rm.release()
         dm.free()
+
+
+def test_class_e_row_block_generated_on_the_device(libspmv, oracle, npb):
+    """BASELINE config 5, class E (na = 9 000 000, 6.3e9 nonzeros: beyond the int32 ABI as
+    one matrix, cg.f cannot even be compiled for it -- CG/globals.h:80-82): a 1/64 row block
+    assembled on the GPU equals the host generator's block bit for bit, and its product
+    matches the oracle element-wise."""
+    import torch
+    cls = npb.cg_class("E")
+    assert cls.na == 9000000 and cls.nonzer == 26
+    lo, hi = cls.na * 17 // 64, cls.na * 18 // 64
+    dm = npb.NpbDeviceMatrix("E", lo, hi, release_vectors=False)
+    a, rowstr, colidx = dm.to_host()
+    ref = npb.NpbMatrix("E", lo, hi)
+    assert dm.nnz == ref.nnz and 0.9 * (hi - lo) * 703 < dm.nnz < 1.1 * (hi - lo) * 703   # 6 326 754 836 / 9e6 per row
+    assert np.array_equal(rowstr, ref.rowstr) and np.array_equal(colidx, ref.colidx) and np.array_equal(a, ref.a)
+    rm = dm.resident()
+    x = np.random.default_rng(64).standard_normal(cls.na)
+    dy = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+    rm.exec(torch.from_numpy(x).cuda(), dy)
+    assert np.array_equal(dy.cpu().numpy(), oracle.spmv(ref.a, x, ref.rowstr, ref.colidx, omp=True))
+    rm.release()
+    dm.free()
+    npb.lib().npb_makea_release_cache()
+
+
+@pytest.mark.parametrize("mode", ["fused", "overlapped", "blocking"])
+def test_peer_exchange_forms_on_the_ring_kernel_single_rank_group(libspmv, oracle, npb, mode):
+    """The three forms of the sharded step on the kernel that can wait for x slices in-kernel
+    (ring layout), with this GPU as its own only peer: the product pushing the slice itself
+    (b200_spmv_exec_pushed), post + sliced product, exchange kernel + product.  Back-to-back
+    steps with changing x and no host synchronisation in between: the epoch flags and the two
+    alternating x buffers alone order the pushes against the products."""
+    import os
+    import torch
+    from lilac_benchmarks_b200 import sharded
+    m = npb.NpbMatrix("A")
+    os.environ["B200_SPMV_PANEL_FMT"] = "2"
+    try:
+        rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel="panel")
+    finally:
+        os.environ.pop("B200_SPMV_PANEL_FMT")
+    assert rm.waits_in_kernel and rm.can_push
+    sh = sharded.PeerShardedSpmv(libspmv, rm, sharded.ShardLayout.build(m.n, 1), 0,
+                                 overlap=mode != "blocking", fused=mode == "fused")
+    assert sh.fused == (mode == "fused") and sh.overlap == (mode != "blocking")
+    try:
+        rng = np.random.default_rng(8)
+        xs = [rng.standard_normal(m.n) for _ in range(4)]
+        refs = [oracle.spmv(m.a, x, m.rowstr, m.colidx) for x in xs]
+        xd = [torch.from_numpy(x).cuda() for x in xs]
+        outs = [sh.step(xd[i % 4]).clone() for i in range(12)]
+        torch.cuda.synchronize()
+        for i, y in enumerate(outs):
+            assert np.array_equal(y.cpu().numpy(), refs[i % 4]), i
+    finally:
+        sh.close()
