@@ -96,7 +96,11 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
+    collect = True
+
     def _sample(self):
+        if not self.collect:
+            return
         nv = self.nv
         self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
         try:
@@ -124,6 +128,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         if self.ok and not self.samples:
             try:
+                self.collect = True
                 self._sample()
             except Exception:
                 pass
@@ -252,18 +257,24 @@ def run_reference_arm(args, world, rank):
 # B200 arm, one GPU
 # --------------------------------------------------------------------------
 def time_steps(torch, step, K, W, barrier, local_rank):
+    """W untimed steps, then exactly K timed ones between two CUDA events on the launching
+    stream.  The clock sampler is created and started BEFORE the warm-up (initialising NVML
+    takes tens of milliseconds of host time: with the GPU idle that long right before the timed
+    region the first timed steps ran ~10 % slow) and only collects during the timed region."""
+    sampler = ClockSampler(local_rank)
+    sampler.collect = False
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(W):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    sampler.collect = True
     e0.record()
     for i in range(K):
         step(i)
     e1.record()
     barrier()
+    sampler.collect = False
     return e0.elapsed_time(e1), sampler.stop()
 
 
@@ -467,8 +478,11 @@ def run_multi_gpu(args, world, rank, local_rank):
     if int(okt.item()) == 0 and psh is not None:
         psh.close()
         psh = None
-    exchange_kind = "nccl" if psh is None else ("peer-fused" if psh.fused else
-                                                 "peer-overlapped" if psh.overlap else "peer")
+    # the peer-memory step has three forms (sharded.PeerShardedSpmv); the fastest on these GPUs
+    # for this block shape is kept, all three are reported
+    peer_forms = psh.calibrate(x_local) if psh is not None else None
+    exchange_kind = "nccl" if psh is None else {"fused": "peer-fused", "overlapped": "peer-overlapped",
+                                                 "blocking": "peer"}[psh.form]
     stepper = psh or sh
 
     # ---- parity: one step, every y element of every rank against the OpenMP oracle ------
@@ -625,6 +639,7 @@ def run_multi_gpu(args, world, rank, local_rank):
                                                "NVLink peer memory; the product waits per slice in-kernel",
                             "peer": "one exchange kernel over NVLink peer memory, then the product",
                             "nccl": "allgather of x per step (NCCL)"}[exchange_kind],
+                        "peer_forms_ms_per_step": peer_forms,
                         "nccl_allgather_variant_ms_per_step": nccl_ms_per_step,
                         "kernel_only_ms_per_step": kernel_only_ms,
                         "same_workload_on_one_gpu": one_gpu,

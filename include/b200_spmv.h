@@ -112,6 +112,13 @@ int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, void *peer_gr
                           const double *v_local, int n_local, int64_t lo, uint64_t epoch,
                           int cols_per_rank);
 
+/* y = A x with a dot product fused into the epilogue: CTA b adds its rows' share of
+ * dotv . y into partial[b], b < b200_spmv_dot_partials(m) (0: this matrix's kernel has no
+ * fused epilogue, b200_spmv_exec_dot returns -1 without launching).  Fixed reduction order.
+ * NPB conj_grad's d = p.q (cg.f:573-576) right where q is produced. */
+int b200_spmv_dot_partials(const b200_matrix *m);
+int b200_spmv_exec_dot(b200_matrix *m, const void *d_x, void *d_y, const void *d_dotv,
+                       void *d_partial, void *stream);
 int b200_spmv_can_push(const b200_matrix *m);    /* 1: b200_spmv_exec_pushed works for this matrix */
 
 /* Upload from DEVICE arrays of the current device (same 1-based contents as the ABI;

@@ -882,6 +882,27 @@ extern "C" int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, vo
     return exec_locked(m, xbuf, d_y, (cudaStream_t)stream, &sf, &xp);
 }
 
+/* y = A x and, in the same launch, partial[b] = (share of CTA b of) dotv . y for the first
+ * b200_spmv_dot_partials(m) entries of `partial`.  Only the paired PANEL kernel has the
+ * fused epilogue; returns -1 without launching otherwise. */
+extern "C" int b200_spmv_dot_partials(const b200_matrix *m)
+{
+    return (m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 0 && m->dtype == B200_F64) ? m->panel.nblk : 0;
+}
+
+extern "C" int b200_spmv_exec_dot(b200_matrix *m, const void *d_x, void *d_y, const void *d_dotv,
+                                  void *d_partial, void *stream)
+{
+    if (!m) die("b200_spmv_exec_dot: null matrix");
+    if (b200_spmv_dot_partials(m) <= 0) return -1;
+    DeviceScope scope(m->device);
+    launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, (cudaStream_t)stream,
+                         (const double *)d_dotv, (double *)d_partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) die("kernel launch failed: %s", cudaGetErrorString(e));
+    return 1;
+}
+
 extern "C" int b200_spmv_can_push(const b200_matrix *m)
 {
     return exec_waits_in_kernel(m) && m->dtype == B200_F64 && m->panel.nblk <= m->ctx->sm_count ? 1 : 0;

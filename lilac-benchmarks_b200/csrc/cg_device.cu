@@ -207,20 +207,32 @@ struct CgBuffers {
 void enqueue_outer_iteration(b200_matrix *m, const CgBuffers &b, int n, cudaStream_t s,
                              int *spmv_count, int *vec_count)
 {
+    const int ndot = b200_spmv_dot_partials(m);
+    const char *fd = getenv("B200_CG_FUSED_DOT");                 /* 0: keep the separate dot kernel */
+    const bool fused_dot = ndot > 0 && ndot <= kBlocks && !(fd && atoi(fd) == 0);
     cg_init_kernel<<<kBlocks, kThreads, 0, s>>>(b.x, b.z, b.p, b.q, b.r, n, b.part_a);
     cg_finish_kernel<<<1, kThreads, 0, s>>>(b.part_a, b.rho + 0);
+    if (fused_dot)      /* entries [ndot, kBlocks) of part_a must read zero for the fused dot */
+        cudaMemsetAsync(b.part_a, 0, kBlocks * sizeof(double), s);
     *vec_count += 2;
     for (int cgit = 0; cgit < 25; ++cgit) {
         const double *rho_old = b.rho + (cgit & 1);
         double *rho_next = b.rho + ((cgit + 1) & 1);
-        b200_spmv_exec(m, b.p, b.q, (void *)s);                                      /* q = A p */
-        cg_dot_kernel<<<kBlocks, kThreads, 0, s>>>(b.p, b.q, n, b.part_a);            /* d = p.q */
+        /* q = A p and d = p.q: in one launch when the product kernel has the fused epilogue
+         * (its CTAs fill the first entries of part_a, the rest stay zero) */
+        if (fused_dot) {
+            b200_spmv_exec_dot(m, b.p, b.q, b.p, b.part_a, (void *)s);
+        } else {
+            b200_spmv_exec(m, b.p, b.q, (void *)s);                                  /* q = A p */
+            cg_dot_kernel<<<kBlocks, kThreads, 0, s>>>(b.p, b.q, n, b.part_a);        /* d = p.q */
+            *vec_count += 1;
+        }
         cg_update_zr_kernel<<<kBlocks, kThreads, 0, s>>>(b.z, b.r, b.p, b.q, n, rho_old, b.part_a,
                                                          nullptr, b.part_b);
         cg_update_p_kernel<<<kBlocks, kThreads, 0, s>>>(b.p, b.r, n, b.part_b, nullptr, rho_old,
                                                         rho_next);
         *spmv_count += 1;
-        *vec_count += 3;
+        *vec_count += 2;
     }
     b200_spmv_exec(m, b.z, b.r, (void *)s);                                          /* r = A z */
     cg_resid_kernel<<<kBlocks, kThreads, 0, s>>>(b.x, b.r, n, b.part_res);

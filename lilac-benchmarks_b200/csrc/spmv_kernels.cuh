@@ -94,9 +94,11 @@ template <typename T>
 void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows,
                        const DevPanel &pm, const uint16_t *seglen, T *val_out, uint16_t *col_out,
                        cudaStream_t s);
-/* y = A x on the panel layout; every row summed left to right */
+/* y = A x on the panel layout; every row summed left to right.  dotv != NULL: CTA b also
+ * writes its share of dotv . y to dot_partial[b] (nblk values, fixed reduction order) */
 template <typename T>
-void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s);
+void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T *dotv = nullptr,
+                  T *dot_partial = nullptr);
 size_t panel_smem_bytes(const DevPanel &pm, bool f32);
 
 /* flagged-stream layout for wide matrices: build passes (spmv_panelg.cu) */

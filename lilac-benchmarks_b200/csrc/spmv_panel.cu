@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(MAXT, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
                   const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
                   const T *__restrict__ x, T *__restrict__ y,
-                  int rows, int ncols, int P, int W, int R, int use_tma, int nbuf)
+                  int rows, int ncols, int P, int W, int R, int use_tma, int nbuf,
+                  const T *__restrict__ dotv, T *__restrict__ dot_partial)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -372,9 +373,31 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         sums[row_cur] = acc;
         __syncthreads();            /* panel p consumed: its x buffer and the sums are free */
     }
+    /* epilogue: the rows of the block, coalesced; optionally the block's share of
+     * dotv . y on the way out (NPB conj_grad's d = p.q, cg.f:573-576: q is in shared memory
+     * right here, so the dot product costs one read of p instead of a kernel of its own).
+     * Fixed order -- per-thread stride, xor-shuffle tree, warp sums left to right --, so the
+     * result is the same on every launch. */
+    T dacc = (T)0;
     for (int i = tid; i < R; i += Tn) {
         const int row = rb * R + i;
-        if (row < rows) y[row] = sums[i];
+        if (row < rows) {
+            const T v = sums[i];
+            y[row] = v;
+            if (dotv) dacc += v * dotv[row];
+        }
+    }
+    if (dotv) {                                           /* block-uniform */
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+        __syncthreads();                                  /* everybody has read its sums */
+        if (lane == 0) sums[warp] = dacc;
+        __syncthreads();
+        if (tid == 0) {
+            T tot = (T)0;
+            for (int w = 0; w < spb; ++w) tot += sums[w];
+            dot_partial[rb] = tot;
+        }
     }
 }
 
@@ -388,7 +411,7 @@ size_t panel_smem_bytes(const DevPanel &pm, bool f32)
 }
 
 template <typename T, int U, int MAXT>
-static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, const T *dotv, T *dot_partial, cudaStream_t s)
 {
     static unsigned attr_set = 0;                  /* function attributes are per device */
     if (!attr_done(&attr_set))
@@ -398,32 +421,32 @@ static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, cudaStream_t 
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
     spmv_panel_kernel<T, U, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const T *>(pm.val), pm.col, pm.meta, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf);
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, dotv, dot_partial);
 }
 
 template <typename T>
-void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s)
+void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T *dotv, T *dot_partial)
 {
     if (pm.nblk <= 0) return;
     const int threads = pm.R / pm.G;
     if (threads <= 128 && pm.U >= 12) {
         /* a handful of warps per SM (NPB class A and smaller: one row per lane, ~100 rows
          * per SM): latency-bound, so each lane keeps 24 pairs of its stream in flight */
-        launch_panel_cfg<T, 12, 128>(pm, x, y, s);
+        launch_panel_cfg<T, 12, 128>(pm, x, y, dotv, dot_partial, s);
     } else if (threads <= 256 && pm.U >= 5) {
         /* few warps per SM (NPB class A / B sized row blocks): the register file
          * is free, so each lane keeps twice as many pairs of the stream in flight */
-        if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, s);
-        else launch_panel_cfg<T, 8, 256>(pm, x, y, s);     /* best on class B (profiles/r01_run23) */
+        if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, dotv, dot_partial, s);
+        else launch_panel_cfg<T, 8, 256>(pm, x, y, dotv, dot_partial, s);     /* best on class B (profiles/r01_run23) */
     } else if (pm.U >= 5) {
-        launch_panel_cfg<T, 5, 512>(pm, x, y, s);
+        launch_panel_cfg<T, 5, 512>(pm, x, y, dotv, dot_partial, s);
     } else if (pm.U == 3) {
-        launch_panel_cfg<T, 3, 512>(pm, x, y, s);
+        launch_panel_cfg<T, 3, 512>(pm, x, y, dotv, dot_partial, s);
     } else {
-        launch_panel_cfg<T, 4, 512>(pm, x, y, s);           /* <= 128 registers per thread */
+        launch_panel_cfg<T, 4, 512>(pm, x, y, dotv, dot_partial, s);           /* <= 128 registers per thread */
     }
 }
-template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t);
-template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t);
+template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t, const double *, double *);
+template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t, const float *, float *);
 
 }  // namespace b200

@@ -274,6 +274,40 @@ class PeerNpbCg:
         self.spmv_count = 0
         self.dist = dist
 
+    def calibrate(self, x_local, steps=20):
+        """Time the forms this matrix supports on the actual GPUs (max over ranks, CUDA events)
+        and keep the fastest; which one wins depends on the rank count and the block shape.
+        Returns {form: ms per step}."""
+        torch = self.torch
+        forms = [("blocking", False, False)]
+        if self.overlap:
+            forms.append(("overlapped", True, False))
+        if self.fused:
+            forms.append(("fused", True, True))
+        best, times = None, {}
+        for name, ov, fu in forms:
+            self.overlap, self.fused = ov, fu
+            for _ in range(3):
+                self.step(x_local)
+            torch.cuda.synchronize()
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.step(x_local)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=self.y_local.device)
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            times[name] = float(t.item())
+            if best is None or times[name] < times[best[0]]:
+                best = (name, ov, fu)
+        self.overlap, self.fused = best[1], best[2]
+        self.form = best[0]
+        return times
+
     def close(self):
         if self.g:
             self.torch.cuda.synchronize()
@@ -402,6 +436,7 @@ class PeerShardedSpmv:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             okf = int(t.item())
         self.fused = bool(okf)
+        self.form = "fused" if self.fused else "overlapped" if self.overlap else "blocking"
 
     def step(self, x_local):
         s = self.torch.cuda.current_stream().cuda_stream
@@ -422,6 +457,40 @@ class PeerShardedSpmv:
             self.L.b200_peer_exchange(self.g, x_local.data_ptr(), self.hi - self.lo, self.lo, e, s)
             self.rm.exec_ptr(self.xfull, self.y_local.data_ptr(), s)
         return self.y_local
+
+    def calibrate(self, x_local, steps=20):
+        """Time the forms this matrix supports on the actual GPUs (max over ranks, CUDA events)
+        and keep the fastest; which one wins depends on the rank count and the block shape.
+        Returns {form: ms per step}."""
+        torch = self.torch
+        forms = [("blocking", False, False)]
+        if self.overlap:
+            forms.append(("overlapped", True, False))
+        if self.fused:
+            forms.append(("fused", True, True))
+        best, times = None, {}
+        for name, ov, fu in forms:
+            self.overlap, self.fused = ov, fu
+            for _ in range(3):
+                self.step(x_local)
+            torch.cuda.synchronize()
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.step(x_local)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=self.y_local.device)
+            if self.dist is not None and self.layout.parts > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            times[name] = float(t.item())
+            if best is None or times[name] < times[best[0]]:
+                best = (name, ov, fu)
+        self.overlap, self.fused = best[1], best[2]
+        self.form = best[0]
+        return times
 
     def close(self):
         if self.g:

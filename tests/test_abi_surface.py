@@ -73,3 +73,24 @@ def test_product_does_not_reference_the_oracle():
             if path.name == "build.py":
                 continue          # builds the checker, never loads it
             assert "liboracle" not in text and "oracle/" not in text, path
+
+
+def test_bench_arms_name_the_workload_identically():
+    """bench.py: `config` must be the same dict in the b200 and the --impl reference arm (the
+    driver compares them), and hold only what names the workload."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = bench.workload_config(bench.workload_label("A"), 14000, 1853104, 14000, 1)
+    assert set(cfg) == {"workload", "rows", "nnz", "ncols", "algorithmic_bytes_per_step", "l2_policy"}
+    assert cfg["algorithmic_bytes_per_step"] == 12 * 1853104 + 4 * 14001 + 16 * 14000
+    proc = subprocess.run(["python", str(ROOT / "bench.py"), "--impl", "reference", "--workload", "A",
+                           "--steps", "2", "--warmup", "1"], stdout=subprocess.PIPE, text=True, check=True,
+                          timeout=600)
+    line = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == cfg
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert bench.workload_label("crsmat170u") == "sparsebench-crsmat170u"
+    assert bench.workload_label("pl22") == "pagerank-powerlaw-2^22"

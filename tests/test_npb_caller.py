@@ -78,3 +78,33 @@ def test_c_caller_loop_issues_the_calls(npb, oracle):
         assert sec > 0.0
         # the last call used xs[(calls - 1) % 3]
         assert np.array_equal(y, oracle.spmv(m.a, xs[(calls - 1) % 3], m.rowstr, m.colidx))
+
+
+def test_generating_vectors_for_the_device_generator(npb):
+    """npb_vectors_get: the sequential part of makea (cg.f:709-718, :876) that
+    include/b200_npb.h consumes -- nonzer or nonzer + 1 entries per vector, positions inside
+    the matrix, the vector's own index forced to 0.5 (vecset, cg.f:991-1019), and the size_i
+    sequence accumulated by repeated multiplication."""
+    import ctypes as C
+    from ctypes import POINTER, c_double, c_int, c_void_p
+    cls = npb.cg_class("S")
+    arow, acol, aelt, size = c_void_p(), c_void_p(), c_void_p(), c_void_p()
+    assert npb.lib().npb_vectors_get(C.byref(cls), C.byref(arow), C.byref(acol), C.byref(aelt), C.byref(size)) == 0
+    n, ld = cls.na, cls.nonzer + 1
+    ar = np.ctypeslib.as_array(C.cast(arow, POINTER(c_int)), shape=(n,))
+    ac = np.ctypeslib.as_array(C.cast(acol, POINTER(c_int)), shape=(n, ld))
+    ae = np.ctypeslib.as_array(C.cast(aelt, POINTER(c_double)), shape=(n, ld))
+    sz = np.ctypeslib.as_array(C.cast(size, POINTER(c_double)), shape=(n,)).copy()
+    npb.lib().npb_free(size)
+    assert set(np.unique(ar)) <= {cls.nonzer, cls.nonzer + 1}
+    for i in (0, 1, n // 2, n - 1):
+        k = ar[i]
+        assert np.all((ac[i, :k] >= 1) & (ac[i, :k] <= n)) and len(set(ac[i, :k])) == k
+        own = np.flatnonzero(ac[i, :k] == i + 1)
+        assert len(own) == 1 and ae[i, own[0]] == 0.5
+    ratio = cls.rcond ** (1.0 / n)
+    assert sz[0] == 1.0 and sz[1] == ratio and sz[2] == ratio * ratio
+    assert abs(sz[-1] * ratio - cls.rcond) < 1e-12
+    # the triples these vectors generate are the matrix: nnz self-check through the host path
+    m = npb.NpbMatrix("S")
+    assert m.nnz == 78148
