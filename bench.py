@@ -48,6 +48,7 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "spmv_algorithmic_bandwidth"
 UNIT = "GB/s"
 L2_BYTES = 126e6
+PRECONDITION = 50       # untimed steps before every timed region, at least (reported in details)
 
 
 def algorithmic_bytes(nnz, rows, ncols, es=8):
@@ -265,7 +266,10 @@ def time_steps(torch, step, K, W, barrier, local_rank):
     sampler.collect = False
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(W):
+    # a short requested warm-up (the driver passes 5) is topped up to PRECONDITION untimed steps:
+    # a few hundred microseconds of work do not bring a GPU that has just idled back to its
+    # steady state (class C: 75.7 us per step over 20 steps after 5 warm-ups, 74.1 us after 50)
+    for i in range(max(W, PRECONDITION)):
         step(i)
     barrier()
     sampler.collect = True
@@ -348,6 +352,7 @@ def run_one_gpu(args):
         "gpu_launches": K * rm.launches_per_exec,
         "config": workload_config(hm.label, hm.n, hm.nnz, ncols, 1),
         "details": {"kernel": rm.kernel_name, "launches_per_step": rm.launches_per_exec,
+                    "untimed_steps_before_timing": max(W, PRECONDITION),
                     "x_vectors_rotated": 4, "resident_bytes": rm.resident_bytes,
                     "gen_s": round(t_gen, 2), "upload_s": round(t_upload, 3)},
         "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s",
@@ -631,6 +636,7 @@ def run_multi_gpu(args, world, rank, local_rank):
             "y_bit_identical": y_ok,
             "config": workload_config(label, n_global, nnz_global, ncols, world),
             "details": {"parallelism": f"{world} equal row blocks, one process per GPU",
+                        "untimed_steps_before_timing": max(W, PRECONDITION),
                         "kernel": kernel_name, "exchange": exchange_kind,
                         "exchange_note": {
                             "peer-fused": "one launch per step: the product kernel stores the rank's x slice into every "

@@ -520,7 +520,12 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         maybe_auto_pin(ov, e.y_bytes);
         /* x: host -> device (gpu.c:264).  Pinned caller memory is read in place over PCIe
          * by a copy kernel on the library's stream (no copy-engine hop); pageable memory
-         * goes through the pinned bounce buffer first. */
+         * goes through the pinned bounce buffer first.  (Letting the product kernel fetch x
+         * itself, chunk by chunk behind flags, so that the transfer overlaps the matrix stream,
+         * was built and measured: a GPU-issued PCIe read takes ~10 us to come back, a window
+         * of chunks in flight serialises on that, and without a window the chunks do not land
+         * in column order -- 208 us per call against 157 us; the fetch state also cost the
+         * class C kernel 10 % at its 128-register limit.  profiles/r02_run13_bench_C*.json) */
         const char *x_pinned = nullptr;       /* host pointer to pinned x, for the copy engine */
         const char *x_alias = nullptr;        /* its device alias, for the copy kernel */
         if (x_used > 0) {

@@ -429,13 +429,10 @@ void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T 
 {
     if (pm.nblk <= 0) return;
     const int threads = pm.R / pm.G;
-    if (threads <= 128 && pm.U >= 12) {
-        /* a handful of warps per SM (NPB class A and smaller: one row per lane, ~100 rows
-         * per SM): latency-bound, so each lane keeps 24 pairs of its stream in flight */
-        launch_panel_cfg<T, 12, 128>(pm, x, y, dotv, dot_partial, s);
-    } else if (threads <= 256 && pm.U >= 5) {
+    if (threads <= 256 && pm.U >= 5) {
         /* few warps per SM (NPB class A / B sized row blocks): the register file
-         * is free, so each lane keeps twice as many pairs of the stream in flight */
+         * is free, so each lane keeps twice as many pairs of the stream in flight (12 pairs
+         * per chunk spill and are no faster: profiles/r02_run6_sweep.txt) */
         if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, dotv, dot_partial, s);
         else launch_panel_cfg<T, 8, 256>(pm, x, y, dotv, dot_partial, s);     /* best on class B (profiles/r01_run23) */
     } else if (pm.U >= 5) {

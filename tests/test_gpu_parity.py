@@ -519,7 +519,7 @@ def test_peer_exchange_spmv_single_rank_group(libspmv, oracle, npb):
         sh.close()
 
 
-@pytest.mark.parametrize("cls", ["W", "A"])
+@pytest.mark.parametrize("cls", ["W", "A", "B"])
 def test_caller_pinned_vectors_through_the_abi(libspmv, oracle, npb, cls):
     """The e2e headline path: x read in place over PCIe from the caller's pinned vector,
     y stored by the kernel straight into the caller's pinned vector (b200_dropin.cu);
@@ -539,8 +539,10 @@ def test_caller_pinned_vectors_through_the_abi(libspmv, oracle, npb, cls):
             keep.append(torch.from_numpy(y).pin_memory())
             y = keep[-1].numpy()
         xv = x[off:]
-        libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
-        assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx)), (x_pinned, y_pinned, off)
+        for rep in range(3):                      # repeated calls: the chunk flags are epochs
+            xv[:] = rng.standard_normal(len(xv))
+            libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
+            assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx, omp=True)), (x_pinned, y_pinned, off, rep)
     assert libspmv.stats()["uploads"] >= 1
 
 
