@@ -56,6 +56,8 @@ struct Part {
     int row_lo, row_hi;
     size_t x_lo, x_hi;         /* byte range of x this device pulls from the host */
     char *d_x, *d_y;           /* full-length x, this block's y */
+    unsigned long long *d_flags;   /* several devices: [nparts] flag[j] = call number whose slice j has landed here */
+    unsigned int *d_counter;       /* ... and the last-block counter of this device's copy kernel */
 };
 
 struct CacheEntry {
@@ -69,6 +71,8 @@ struct CacheEntry {
     int nparts;
     Part part[kMaxDevices];
     int ncols;
+    int cols_per_part;         /* several devices: columns of x each device pulls (uniform) */
+    unsigned long long epoch;  /* ... and the call number the flags carry */
     void *h_x, *h_y;           /* pinned bounce buffers (portable, mapped) */
     size_t x_bytes, y_bytes;
 };
@@ -387,6 +391,8 @@ static void release_entry_locked(CacheEntry &e)
         release_locked(pt.m);
         cudaFree(pt.d_x);
         cudaFree(pt.d_y);
+        cudaFree(pt.d_flags);
+        cudaFree(pt.d_counter);
     }
     if (e.h_x) cudaFreeHost(e.h_x);
     if (e.h_y) cudaFreeHost(e.h_y);
@@ -406,6 +412,7 @@ static void build_entry_locked(CacheEntry &e)
         pt.ctx = ctx_for_device_locked(multi ? g_devs[p] : g_devs[0]);
         pt.row_lo = bounds[p]; pt.row_hi = bounds[p + 1];
         pt.m = nullptr; pt.d_x = pt.d_y = nullptr;
+        pt.d_flags = nullptr; pt.d_counter = nullptr;
         if (pt.row_hi > pt.row_lo || !multi) {
             /* a row block is addressed exactly as the ABI would: (a, rowstr + lo, colidx, hi - lo) */
             pt.m = upload_locked(pt.ctx, e.a, e.rowstr + pt.row_lo, e.colidx, pt.row_hi - pt.row_lo,
@@ -416,14 +423,24 @@ static void build_entry_locked(CacheEntry &e)
     e.x_bytes = (size_t)std::max(e.ncols, 1) * es;
     e.y_bytes = (size_t)std::max(e.rows, 1) * es;
     const size_t x_used = (size_t)e.ncols * es;
+    /* slice of x each device fetches: the same number of columns everywhere (the product
+     * kernels map a column to the device that delivers it by one division), 16-byte granules */
+    const int gran = (int)(16 / es);
+    e.cols_per_part = std::max(gran, ((e.ncols + e.nparts - 1) / e.nparts + gran - 1) / gran * gran);
+    e.epoch = 0;
     for (int p = 0; p < e.nparts; ++p) {
         Part &pt = e.part[p];
         DeviceScope scope(pt.ctx->device);
-        /* slice of x this device fetches: 16-byte granules */
-        pt.x_lo = p == 0 ? 0 : (x_used * (size_t)p / e.nparts) / 16 * 16;
-        pt.x_hi = p == e.nparts - 1 ? x_used : (x_used * (size_t)(p + 1) / e.nparts) / 16 * 16;
+        pt.x_lo = std::min(x_used, (size_t)p * e.cols_per_part * es);
+        pt.x_hi = std::min(x_used, (size_t)(p + 1) * e.cols_per_part * es);
         CUDA_OK(cudaMalloc((void **)&pt.d_x, std::max<size_t>(e.x_bytes, 16)));
         CUDA_OK(cudaMalloc((void **)&pt.d_y, std::max<size_t>((size_t)(pt.row_hi - pt.row_lo) * es, 16)));
+        if (multi) {
+            CUDA_OK(cudaMalloc((void **)&pt.d_flags, kMaxDevices * sizeof(unsigned long long)));
+            CUDA_OK(cudaMemset(pt.d_flags, 0, kMaxDevices * sizeof(unsigned long long)));
+            CUDA_OK(cudaMalloc((void **)&pt.d_counter, sizeof(unsigned int)));
+            CUDA_OK(cudaMemset(pt.d_counter, 0, sizeof(unsigned int)));
+        }
     }
     CUDA_OK(cudaHostAlloc(&e.h_x, e.x_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     CUDA_OK(cudaHostAlloc(&e.h_y, e.y_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
@@ -546,55 +563,74 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
 
         const bool multi = e.nparts > 1;
+        /* one cudaSetDevice per device and loop, restored once at the end: with eight devices
+         * the host side of a call is a few dozen runtime calls, and it is the critical path
+         * (the first version -- a device scope per step, an event per slice and 56 stream
+         * waits -- spent 0.24 ms of a 0.51 ms call in the runtime) */
+        int saved_dev = -1, cur_dev = -1;
+        cudaGetDevice(&saved_dev);
+        cur_dev = saved_dev;
+        auto use = [&](int d) { if (d != cur_dev) { CUDA_OK(cudaSetDevice(d)); cur_dev = d; } };
+        const unsigned long long epoch = ++e.epoch;
         for (int p = 0; p < e.nparts; ++p) {
             Part &pt = e.part[p];
-            DeviceScope scope(pt.ctx->device);
+            use(pt.ctx->device);
             cudaStream_t s = pt.ctx->stream;
-            if (pt.x_hi > pt.x_lo) {
-                const size_t bytes = pt.x_hi - pt.x_lo;
-                if (g_zero_copy || multi) {
-                    /* one kernel: read the slice over this device's PCIe link, store it into
-                     * every device's x buffer (the peers' over NVLink) */
-                    void *dst[kMaxDevices];
-                    for (int j = 0; j < e.nparts; ++j) dst[j] = e.part[j].d_x + pt.x_lo;
-                    launch_copy_in_multi(x_alias + pt.x_lo, dst, e.nparts, bytes, s);
+            const size_t bytes = pt.x_hi - pt.x_lo;
+            if (multi) {
+                /* one kernel: read the slice over this device's PCIe link, store it into every
+                 * device's x buffer (the peers' over NVLink), then publish the call number on
+                 * every device's flag for this slice -- the products wait on flags, not events */
+                void *dst[kMaxDevices];
+                unsigned long long *flag[kMaxDevices];
+                for (int j = 0; j < e.nparts; ++j) {
+                    dst[j] = e.part[j].d_x + pt.x_lo;
+                    flag[j] = e.part[j].d_flags + p;
+                }
+                launch_copy_in_multi_flagged(x_alias ? x_alias + pt.x_lo : nullptr, dst, e.nparts, bytes, flag,
+                                             epoch, pt.d_counter, s);
+            } else if (bytes > 0) {
+                if (g_zero_copy) {
+                    void *dst[1] = {pt.d_x + pt.x_lo};
+                    launch_copy_in_multi(x_alias + pt.x_lo, dst, 1, bytes, s);
                 } else {
                     CUDA_OK(cudaMemcpyAsync(pt.d_x + pt.x_lo, x_pinned + pt.x_lo, bytes, cudaMemcpyHostToDevice, s));
                 }
             }
-            if (multi) CUDA_OK(cudaEventRecord(pt.ctx->ev_x, s));
         }
         int launched = 0;
+        int timed_part = -1;
         for (int p = 0; p < e.nparts; ++p) {
             Part &pt = e.part[p];
-            DeviceScope scope(pt.ctx->device);
-            cudaStream_t s = pt.ctx->stream;
-            if (multi)
-                for (int j = 0; j < e.nparts; ++j)
-                    if (j != p) CUDA_OK(cudaStreamWaitEvent(s, e.part[j].ctx->ev_x, 0));
             const int prow = pt.row_hi - pt.row_lo;
             if (!pt.m || prow <= 0) continue;
-            if (g_time_kernels) CUDA_OK(cudaEventRecord(pt.ctx->ev0, s));
+            use(pt.ctx->device);
+            cudaStream_t s = pt.ctx->stream;
+            /* kernel timing: every call on one device; on several, the first block only */
+            const bool timed = g_time_kernels && timed_part < 0;
+            if (timed) { CUDA_OK(cudaEventRecord(pt.ctx->ev0, s)); timed_part = p; }
             char *y_target = nullptr;
             if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
                 y_target = y_alias + (size_t)pt.row_lo * es;
-            launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, nullptr);
-            if (g_time_kernels) CUDA_OK(cudaEventRecord(pt.ctx->ev1, s));
+            if (multi && exec_waits_in_kernel(pt.m)) {
+                /* the ring kernel waits per slice, just before the panels that need it */
+                SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts};
+                launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
+            } else {
+                if (multi) launch_wait_flags(pt.d_flags, e.nparts, epoch, s);
+                launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, nullptr);
+            }
+            if (timed) CUDA_OK(cudaEventRecord(pt.ctx->ev1, s));
             if (!y_target)
                 CUDA_OK(cudaMemcpyAsync(y_host + (size_t)pt.row_lo * es, pt.d_y, (size_t)prow * es,
                                         cudaMemcpyDeviceToHost, s));
         }
         float kernel_ms = 0.f;
-        for (int p = 0; p < e.nparts; ++p) {
-            Part &pt = e.part[p];
-            DeviceScope scope(pt.ctx->device);
-            CUDA_OK(cudaStreamSynchronize(pt.ctx->stream));
-            if (g_time_kernels && pt.m && pt.row_hi > pt.row_lo) {
-                float ms = 0.f;
-                CUDA_OK(cudaEventElapsedTime(&ms, pt.ctx->ev0, pt.ctx->ev1));
-                kernel_ms = std::max(kernel_ms, ms);
-            }
-        }
+        for (int p = 0; p < e.nparts; ++p)
+            CUDA_OK(cudaStreamSynchronize(e.part[p].ctx->stream));
+        if (timed_part >= 0)
+            CUDA_OK(cudaEventElapsedTime(&kernel_ms, e.part[timed_part].ctx->ev0, e.part[timed_part].ctx->ev1));
+        use(saved_dev);
         if (!y_direct) memcpy(ov, e.h_y, (size_t)n * es);
         g_stats.kernel_ms += kernel_ms;
         g_stats.kernel_launches += (uint64_t)launched;

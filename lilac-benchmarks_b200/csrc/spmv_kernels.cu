@@ -325,6 +325,79 @@ __global__ void copy_in_multi_kernel(const unsigned char *__restrict__ src, Copy
     }
 }
 
+struct CopyFlags { unsigned long long *p[8]; unsigned long long epoch; unsigned int *counter; };
+
+__global__ void copy_in_multi_flagged_kernel(const unsigned char *__restrict__ src, CopyDst dst, size_t bytes,
+                                             int vec, CopyFlags fl)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t done = 0;
+    if (vec) {
+        const size_t n16 = bytes / 16;
+        for (size_t i = t0; i < n16; i += stride) {
+            const int4 v = reinterpret_cast<const int4 *>(src)[i];
+            for (int j = 0; j < dst.n; ++j) reinterpret_cast<int4 *>(dst.p[j])[i] = v;
+        }
+        done = n16 * 16;
+    }
+    for (size_t i = done + t0; i < bytes; i += stride) {
+        const unsigned char v = src[i];
+        for (int j = 0; j < dst.n; ++j) dst.p[j][i] = v;
+    }
+    /* the block that arrives last publishes: everybody's (peer) stores precede its release */
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(fl.counter, 1u);
+        last = prev == gridDim.x - 1;
+        if (last) *fl.counter = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int j = 0; j < dst.n; ++j)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl.p[j]), "l"(fl.epoch) : "memory");
+    }
+}
+
+void launch_copy_in_multi_flagged(const void *src, void *const *dst, int ndst, size_t bytes,
+                                  unsigned long long *const *flag, unsigned long long epoch,
+                                  unsigned int *counter, cudaStream_t s)
+{
+    if (ndst <= 0) return;
+    CopyDst d;
+    CopyFlags f;
+    d.n = ndst > 8 ? 8 : ndst;
+    uintptr_t al = reinterpret_cast<uintptr_t>(src);
+    for (int j = 0; j < d.n; ++j) {
+        d.p[j] = static_cast<unsigned char *>(dst[j]);
+        f.p[j] = flag[j];
+        al |= reinterpret_cast<uintptr_t>(dst[j]);
+    }
+    f.epoch = epoch;
+    f.counter = counter;
+    const int grid = (int)std::min<size_t>((bytes / 16 + 255) / 256 + 1, 148 * 4);
+    copy_in_multi_flagged_kernel<<<grid, 256, 0, s>>>(static_cast<const unsigned char *>(src), d, bytes,
+                                                      (al & 15) == 0 ? 1 : 0, f);
+}
+
+__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long epoch)
+{
+    if ((int)threadIdx.x < n) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while (v < epoch);
+    }
+}
+
+void launch_wait_flags(const unsigned long long *flags, int n, unsigned long long epoch, cudaStream_t s)
+{
+    if (n > 0) wait_flags_kernel<<<1, 32, 0, s>>>(flags, n, epoch);
+}
+
 void launch_copy_in_multi(const void *src, void *const *dst, int ndst, size_t bytes, cudaStream_t s)
 {
     if (bytes == 0 || ndst <= 0) return;

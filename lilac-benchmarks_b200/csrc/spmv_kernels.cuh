@@ -58,6 +58,14 @@ void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s);
 /* the same with up to 8 destinations (the local buffer and the peers' over NVLink):
  * the source is read once.  All pointers 16-byte aligned relative to each other. */
 void launch_copy_in_multi(const void *src, void *const *dst, int ndst, size_t bytes, cudaStream_t s);
+/* ... and, once every block's stores are out, flag[j][0] = epoch for every destination j
+ * (st.release.sys; `counter` is a zeroed device word used to find the last block): consumers
+ * on the destination devices wait on their flag instead of on a CUDA event */
+void launch_copy_in_multi_flagged(const void *src, void *const *dst, int ndst, size_t bytes,
+                                  unsigned long long *const *flag, unsigned long long epoch,
+                                  unsigned int *counter, cudaStream_t s);
+/* spin (one warp) until flags[i] >= epoch for all i < n: for kernels that cannot wait themselves */
+void launch_wait_flags(const unsigned long long *flags, int n, unsigned long long epoch, cudaStream_t s);
 
 /* ------------------------------------------------------------------------
  * PANEL: private column-panel layout (built once at upload, on the device);

@@ -112,3 +112,20 @@ def test_abi_mode_with_one_listed_device_is_the_single_device_path(tmp_path):
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0 and "abi multi ok" in proc.stdout, proc.stdout[-4000:]
+
+
+@needs_two
+def test_npb_cg_binary_drives_two_gpus_unchanged(libspmv):
+    """The compiled NPB CG caller (callers/npb: the C restatement of NPB3.3.1/CG/cg.f, the
+    reference's primary caller of the ABI) dlopens libb200-spmv and, with nothing but
+    B200_SPMV_DEVICES in its environment, runs class B on two GPUs: zeta verifies
+    (cg.f:363-368; exit status 0) and the library reports two devices."""
+    cg = ROOT / "lilac-benchmarks_b200" / "callers" / "cg"
+    if not cg.exists():
+        pytest.skip("callers/cg not built")
+    env = dict(os.environ, B200_SPMV_DEVICES="0,1", B200_SPMV_VERBOSE="1")
+    proc = subprocess.run([str(cg), "B", str(libspmv.B200_SO)], env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert "spread over 2 devices" in proc.stderr, proc.stderr[-2000:]
+    assert "SUCCESSFUL" in proc.stdout.upper(), proc.stdout[-2000:]
