@@ -228,11 +228,16 @@ def run_reference_arm(args, world, rank):
     ncols = int(hm.colidx.max())
     x = np.random.default_rng(1234).random(ncols + 2)
     B = algorithmic_bytes(hm.nnz, hm.n, ncols)
-    # bound the run to about a minute of products: native is ~7.5 GB/s on one core
-    est = B / 7.0e9
+    # bound the run to about a minute of products: time one first (class D gathers from a 12 MB x
+    # run at 1-3 GB/s on one core, class C at 7-10 GB/s), then size the sample
+    oracle = entry.load_oracle()
+    use_ref = oracle.ref_available()
+    t1 = time.perf_counter()
+    oracle.spmv(hm.a, x, hm.rowstr, hm.colidx, use_ref=use_ref)
+    est = max(time.perf_counter() - t1, 1e-4)
     steps = max(1, min(max(args.steps, 1), int(40.0 / est) or 1, 200))
-    warmup = max(1, min(args.warmup, 3, int(10.0 / est) or 1))
-    dt, kind, cores, _ = cpu_reference_spmv(hm.a, hm.rowstr, hm.colidx, x, steps, warmup)
+    warmup = max(1, min(max(args.warmup, 1), int(10.0 / est) or 1))     # the sizing product is the first
+    dt, kind, cores, _ = cpu_reference_spmv(hm.a, hm.rowstr, hm.colidx, x, steps, warmup - 1)
     dt_omp, _, cores_omp, _ = cpu_reference_spmv(hm.a, hm.rowstr, hm.colidx, x, max(1, min(steps, 50)), 1, omp=True)
     val = B / dt / 1e9
     sample = f"whole {hm.label} matrix, {steps} products of {dt * 1e3:.1f} ms"
