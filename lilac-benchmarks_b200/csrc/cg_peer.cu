@@ -4,11 +4,14 @@
  * the exchange replaces what an MPI / NCCL version would do with an allgather
  * of p and two allreduces per CG iteration.
  *
- * Memory model: data stores to peers are plain st.global; after its stores a
- * block executes __threadfence_system() and bumps a local counter; the block
- * that finishes last publishes the epoch to every rank with st.release.sys.
- * Consumers spin with ld.acquire.sys.  One rank per GPU, so a spinning kernel
- * never waits on work queued behind it on its own device.
+ * Memory model: data stores to peers are plain st.global; after the CTA barrier
+ * that follows a block's stores ONE thread executes __threadfence_system() (the
+ * barrier makes the fence cumulative over the block's stores) and bumps a local
+ * counter; the block that finishes last fences once more and publishes the epoch
+ * to every rank with relaxed system-scope stores (fence + relaxed store = release;
+ * a st.release.sys per rank would pay the fence -- an NVLink round trip -- once
+ * per rank).  Consumers spin with ld.acquire.sys.  One rank per GPU, so a
+ * spinning kernel never waits on work queued behind it on its own device.
  */
 #include "../../include/b200_peer.h"
 #include "spmv_kernels.cuh"
@@ -49,9 +52,12 @@ struct PeerDev {
     double *partial;                    /* local: kBlocks doubles */
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+/* release = ONE system-scope fence, then relaxed stores: a st.release.sys per destination
+ * repeats the fence -- a round trip over NVLink each -- once per rank (the exchange kernel took
+ * 50 us on 4 GPUs against 11 us on one, profiles/r02_run20_step_breakdown_n4.txt) */
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -76,21 +82,24 @@ __device__ __forceinline__ double block_sum(double v)
     return s;
 }
 
-/* true in every thread of the block that arrives last (all other blocks'
- * earlier global / peer stores are then visible to it and ordered before
- * whatever it publishes) */
+/* true in every thread of the block that arrives last.  One thread per block fences at system
+ * scope after the CTA barrier (causality is cumulative: the barrier orders the other threads'
+ * stores before it), not every thread; the last block fences once more (acquire side of the
+ * counter, release side of whatever it publishes next with relaxed stores). */
 __device__ __forceinline__ bool last_block(unsigned int *counter)
 {
     __shared__ bool last;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int prev = atomicAdd(counter, 1u);
         last = prev == gridDim.x - 1;
-        if (last) *counter = 0;                  /* ready for the next launch */
+        if (last) {
+            *counter = 0;                        /* ready for the next launch */
+            __threadfence_system();
+        }
     }
     __syncthreads();
-    if (last) __threadfence_system();
     return last;
 }
 
@@ -133,7 +142,7 @@ __device__ __forceinline__ void publish_scalar(const PeerDev &g, int slot, unsig
             for (int w = 0; w < kThreads / 32; ++w) tot += wsum[w];
             for (int j = 0; j < g.nranks; ++j) g.scal[j][slot * NR + g.rank] = tot;
             __threadfence_system();
-            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.sflag[j] + slot * NR + g.rank, e);
+            for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.sflag[j] + slot * NR + g.rank, e);
         }
     }
 }
@@ -174,8 +183,8 @@ peer_push_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
     }
-    if (last_block(g.counter + 0) && threadIdx.x == 0)
-        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+    if (last_block(g.counter + 0) && threadIdx.x == 0)       /* fenced by last_block */
+        for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.vflag[j] + g.rank, e);
 }
 
 /* One launch per product for back-to-back products (b200_peer_exchange): report the
@@ -189,7 +198,7 @@ peer_exchange_kernel(PeerDev g, const double *__restrict__ v, int n, long long l
     if (e > 1) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             __threadfence_system();
-            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e - 1);
+            for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.rflag[j] + g.rank, e - 1);
         }
         wait_flags(g.rflag[g.rank], g.nranks, e - 1);
     }
@@ -202,8 +211,8 @@ peer_exchange_kernel(PeerDev g, const double *__restrict__ v, int n, long long l
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = val;
     }
     if (last_block(g.counter + 0)) {
-        if (threadIdx.x == 0)
-            for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+        if (threadIdx.x == 0)                                /* fenced by last_block */
+            for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.vflag[j] + g.rank, e);
         wait_flags(g.vflag[g.rank], g.nranks, e);
     }
 }
@@ -218,7 +227,7 @@ peer_post_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
 {
     if (e > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
-        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e - 1);
+        for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.rflag[j] + g.rank, e - 1);
     }
     if (e > 2) wait_flags(g.rflag[g.rank], g.nranks, e - 2);
     double *const *dstv = (e & 1) ? g.xalt : g.xfull;
@@ -231,8 +240,8 @@ peer_post_kernel(PeerDev g, const double *__restrict__ v, int n, long long lo, u
         const double val = v[i];
         for (int j = 0; j < g.nranks; ++j) dstv[j][lo + i] = val;
     }
-    if (last_block(g.counter + 4) && threadIdx.x == 0)
-        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e);
+    if (last_block(g.counter + 4) && threadIdx.x == 0)       /* fenced by last_block */
+        for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.vflag[j] + g.rank, e);
 }
 
 __global__ void peer_wait_vector_kernel(PeerDev g, unsigned long long e)
@@ -245,7 +254,7 @@ __global__ void peer_consumed_kernel(PeerDev g, unsigned long long e)
 {
     if (threadIdx.x == 0) {
         __threadfence_system();
-        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.rflag[j] + g.rank, e);
+        for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.rflag[j] + g.rank, e);
     }
 }
 
@@ -304,8 +313,8 @@ peer_update_p_kernel(PeerDev g, double *p, const double *__restrict__ r, int n, 
         p[i] = pi;
         for (int j = 0; j < g.nranks; ++j) g.xfull[j][lo + i] = pi;
     }
-    if (last_block(g.counter + 3) && threadIdx.x == 0)
-        for (int j = 0; j < g.nranks; ++j) st_release_sys(g.vflag[j] + g.rank, e_vec);
+    if (last_block(g.counter + 3) && threadIdx.x == 0)       /* fenced by last_block */
+        for (int j = 0; j < g.nranks; ++j) st_relaxed_sys(g.vflag[j] + g.rank, e_vec);
 }
 
 __global__ void __launch_bounds__(kThreads)

@@ -62,9 +62,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     return v;
 }
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+/* after a __threadfence_system(): fence + relaxed store is a release without a fence per store */
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 /* host side: true when the calling device has been seen before (bit per device ordinal);

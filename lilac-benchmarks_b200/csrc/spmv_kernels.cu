@@ -345,20 +345,18 @@ __global__ void copy_in_multi_flagged_kernel(const unsigned char *__restrict__ s
         const unsigned char v = src[i];
         for (int j = 0; j < dst.n; ++j) dst.p[j][i] = v;
     }
-    /* the block that arrives last publishes: everybody's (peer) stores precede its release */
-    __shared__ bool last;
-    __threadfence_system();
+    /* the block that arrives last publishes: one system-scope fence per block after the
+     * barrier (cumulative), one more in the last block, then relaxed flag stores */
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(fl.counter, 1u);
-        last = prev == gridDim.x - 1;
-        if (last) *fl.counter = 0;
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
         __threadfence_system();
-        for (int j = 0; j < dst.n; ++j)
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl.p[j]), "l"(fl.epoch) : "memory");
+        const unsigned int prev = atomicAdd(fl.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *fl.counter = 0;
+            __threadfence_system();
+            for (int j = 0; j < dst.n; ++j)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fl.p[j]), "l"(fl.epoch) : "memory");
+        }
     }
 }
 

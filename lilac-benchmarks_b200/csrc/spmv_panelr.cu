@@ -170,7 +170,7 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
     if (xp.src) {
         if (blockIdx.x == 0 && tid == 0 && xp.epoch > 1) {
             __threadfence_system();
-            for (int j = 0; j < xp.nranks; ++j) st_release_sys_u64(xp.rflag[j] + xp.rank, xp.epoch - 1);
+            for (int j = 0; j < xp.nranks; ++j) st_relaxed_sys_u64(xp.rflag[j] + xp.rank, xp.epoch - 1);
         }
         if (xp.epoch > 2) {
             if (tid < xp.nranks)
@@ -199,14 +199,17 @@ spmv_panelr_kernel(const unsigned char *__restrict__ stream,
                         reinterpret_cast<int4 *>(static_cast<char *>(xp.dst[j]) + xp.offset)[i] = v[q];
             }
         }
-        __threadfence_system();
+        /* one system-scope fence per CTA after the barrier (cumulative), one more in the CTA
+         * that arrives last, then relaxed flag stores: a st.release.sys per rank would repeat
+         * the fence -- an NVLink round trip -- once per rank */
         __syncthreads();
         if (tid == 0) {
+            __threadfence_system();
             const unsigned int prev = atomicAdd(xp.counter, 1u);
             if (prev == gridDim.x - 1) {                      /* everybody's stores are out */
                 *xp.counter = 0;
                 __threadfence_system();
-                for (int j = 0; j < xp.nranks; ++j) st_release_sys_u64(xp.vflag[j] + xp.rank, xp.epoch);
+                for (int j = 0; j < xp.nranks; ++j) st_relaxed_sys_u64(xp.vflag[j] + xp.rank, xp.epoch);
             }
         }
     }
