@@ -296,6 +296,11 @@ def run_one_gpu(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     libspmv.lib().b200_spmv_init(0)
+    if args.abi_devices > 1:
+        # the end-to-end legs (and the callers) go through spmv_harness_ spread over this many
+        # GPUs by one process (ABI mode); `value` stays the one-GPU kernel
+        ndev = min(args.abi_devices, torch.cuda.device_count())
+        os.environ["B200_SPMV_DEVICES"] = ",".join(str(d) for d in range(ndev))
     K, W = max(args.steps, 1), max(args.warmup, 3)
     rng = np.random.default_rng(1234)
     name = args.workload or "C"
@@ -331,12 +336,21 @@ def run_one_gpu(args):
     st = libspmv.stats()
     h2d, d2h = st["h2d_bytes"] // Ke, st["d2h_bytes"] // Ke
     e2e_kernel_ms = st["kernel_ms"] / Ke
+    e2e_devices = libspmv.devices_in_use()
+    e2e_y = hy_np.copy()                       # result of the last call: x = hx_np[(Ke - 1) & 3]
     # pageable caller vectors (what NPB's COMMON arrays / pagerank's std::vectors are): pinned
     # bounce buffers inside the library, filled by its copy threads
     px = [np.array(v) for v in hx_np]
     py = np.zeros(hm.n)
     npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, 3)
     e2e_pageable_sec = npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, min(Ke, 500))
+    # ... and the same pageable vectors with B200_SPMV_PIN_HOST=3 (opt-in): the library registers a
+    # vector on its third sighting and checks the mapping on every call
+    libspmv.lib().b200_spmv_set_auto_pin(3)
+    npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, 16)
+    e2e_autopin_sec = npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, min(Ke, 500))
+    libspmv.lib().b200_spmv_set_auto_pin(0)      # gives the registrations back ...
+    libspmv.lib().b200_spmv_set_auto_pin(int(os.environ.get("B200_SPMV_PIN_HOST", "0") or 0))   # ... and restores the setting
     t0 = time.perf_counter()
     for i in range(min(Ke, 200)):
         libspmv.spmv_harness(hy_np, hm.a, hx_np[i & 3], hm.rowstr, hm.colidx, hm.n)
@@ -366,10 +380,13 @@ def run_one_gpu(args):
                      "peak_source": peak_src, "kernel": f"spmv ({rm.kernel_name})"},
         "e2e": {"value": B / e2e_sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3, "steps": Ke,
-                "api": "spmv_harness_ called from the C caller loop (callers/npb), pinned caller vectors",
+                "api": "spmv_harness_ called from the C caller loop (callers/npb), pinned caller vectors"
+                       + (f", one process driving {e2e_devices} GPUs (B200_SPMV_DEVICES)" if e2e_devices > 1 else ""),
+                "devices": e2e_devices,
                 "kernel_ms_per_step": e2e_kernel_ms,
                 "pageable_ms_per_step": e2e_pageable_sec * 1e3,
                 "pageable_value": B / e2e_pageable_sec / 1e9,
+                "pageable_pin_host_3_ms_per_step": e2e_autopin_sec * 1e3,
                 "python_ctypes_ms_per_step": e2e_python_sec * 1e3},
         "clocks": clocks,
     }
@@ -423,6 +440,13 @@ def run_one_gpu(args):
         line["cpu_baseline_omp"] = {
             "value": B / dt_omp / 1e9, "unit": UNIT, "cores": cores_omp, "kind": "port",
             "note": "row-parallel OpenMP loop, stand-in for libspmv/mkl.c (MKL not in image)"}
+        # the end-to-end leg's own result against the oracle (its last call)
+        oracle = entry.load_oracle()
+        y_e2e_ref = oracle.spmv(hm.a, np.ascontiguousarray(hx_np[(Ke - 1) % len(hx_np)]), hm.rowstr, hm.colidx, omp=True)
+        nz2 = y_e2e_ref != 0
+        line["e2e"]["y_bit_identical"] = bool(np.array_equal(e2e_y, y_e2e_ref))
+        line["e2e"]["y_max_rel_diff"] = (float(np.max(np.abs(e2e_y - y_e2e_ref)[nz2] / np.abs(y_e2e_ref)[nz2]))
+                                         if nz2.any() else 0.0)
     print(json.dumps(line), flush=True)
 
 
@@ -689,6 +713,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the parity check")
     ap.add_argument("--no-e2e", action="store_true", help="N>1: skip the ABI-mode end-to-end leg")
     ap.add_argument("--cpu-steps", type=int, default=120)
+    ap.add_argument("--abi-devices", type=int, default=1,
+                    help="N=1 run: spread the end-to-end (spmv_harness_) legs over this many GPUs (ABI mode)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -172,13 +172,22 @@ typedef struct {
     double   upload_ms;        /* wall time of the uploads */
     uint64_t h2d_bytes;        /* x traffic */
     uint64_t d2h_bytes;        /* y traffic */
+    uint64_t auto_pinned_calls;   /* calls that moved x or y through a vector this library registered */
+    uint64_t auto_pin_revoked;    /* registrations dropped because the owner had remapped the memory */
 } b200_spmv_stats;
 void b200_spmv_get_stats(b200_spmv_stats *out);
 void b200_spmv_reset_stats(void);
 
-/* Pin a caller-owned host vector so x / y move by direct DMA instead of the
- * library's pinned bounce buffer.  Only for buffers that outlive the library
- * use (NPB's COMMON vectors, pagerank's two std::vectors). */
+/* Pin a caller-owned host vector so x / y move in place over PCIe instead of through the
+ * library's pinned bounce buffer (class C: 0.15 ms per call instead of 0.29 ms).  Either the
+ * owner does it (b200_spmv_pin_host, or its own cudaHostAlloc / cudaHostRegister), or the
+ * library does: with B200_SPMV_PIN_HOST=N / b200_spmv_set_auto_pin(N), N > 0, the drop-in
+ * symbols register a vector once they have seen it N times at the same address (NPB's COMMON
+ * vectors, pagerank's two std::vectors), and verify on every call -- sample words of x and y
+ * as seen through the GPU mapping against the host's view -- that its owner has not remapped
+ * the memory; a stale registration is dropped and the call redone through the bounce buffer.
+ * Off by default: see b200_dropin.cu.  set_auto_pin(0) unregisters everything again. */
+void b200_spmv_set_auto_pin(int sightings);
 int b200_spmv_pin_host(void *ptr, size_t bytes);
 int b200_spmv_unpin_host(void *ptr);
 

@@ -86,6 +86,15 @@ static b200_spmv_stats g_stats;
 static bool g_conf_ready = false;
 static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 1;
 static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
+
+/* caller vectors seen by the drop-in path (B200_SPMV_PIN_HOST) */
+struct AutoPin { char *lo, *hi; int seen; bool registered; bool failed; uint64_t last_use; };
+static std::vector<AutoPin> g_auto;
+/* what the probe kernels report about an auto-registered vector (pinned, mapped) */
+struct PinProbe { int x_bad; int pad; unsigned long long y_val[4]; };
+static PinProbe *g_probe = nullptr;
+struct RegSpan { char *lo, *hi; };              /* page-aligned host ranges registered by maybe_auto_pin */
+static std::vector<RegSpan> g_spans;
 static int g_ndev = 0, g_devs[kMaxDevices];
 static int64_t g_multi_min_nnz = 1 << 22;
 
@@ -250,7 +259,9 @@ static void ensure_conf_locked(void)
     g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
     g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
     g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
-    g_auto_pin = env_int("B200_SPMV_PIN_HOST", 0);
+    g_auto_pin = std::max(0, env_int("B200_SPMV_PIN_HOST", 0));
+    CUDA_OK(cudaHostAlloc((void **)&g_probe, sizeof(PinProbe), cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(g_probe, 0, sizeof(PinProbe));
     g_guard = env_int("B200_SPMV_GUARD", 1);
     {
         const char *v = getenv("B200_SPMV_MULTI_MIN_NNZ");
@@ -364,18 +375,123 @@ static int register_range_locked(void *p, size_t bytes)
     return 0;
 }
 
-/* B200_SPMV_PIN_HOST=1: register a caller vector the first time it is seen, so later calls
- * move it in place instead of through the bounce buffer.  Only safe for vectors that
- * outlive the library use (NPB's COMMON arrays, pagerank's two std::vectors): a range
- * that is freed and mapped again while registered would be read through a stale
- * mapping.  Off by default for that reason. */
-static void maybe_auto_pin(const void *p, size_t bytes)
+static bool spans_intersect(const void *p, size_t bytes)
 {
-    if (!g_auto_pin || bytes == 0) return;
+    const char *lo = (const char *)p, *hi = lo + bytes;
+    for (const RegSpan &sp : g_spans)
+        if (lo < sp.hi && sp.lo < hi) return true;
+    return false;
+}
+
+static bool spans_cover(const void *p, size_t bytes)
+{
+    const char *lo = (const char *)p, *hi = lo + bytes;
+    for (const RegSpan &sp : g_spans)
+        if (lo >= sp.lo && hi <= sp.hi) return true;
+    return false;
+}
+
+/* B200_SPMV_PIN_HOST=N / b200_spmv_set_auto_pin(N) (default 0: never): a caller vector seen
+ * N times at the same address with the same length is registered (cudaHostRegister), so that
+ * later calls move it in place over PCIe instead of through the bounce buffer -- NPB's COMMON
+ * vectors, pagerank's two std::vectors, SparseBench's static work arrays all come back call
+ * after call; bfs, whose vectors are new on every call, never qualifies with N >= 2.  The hazard
+ * of registering memory one does not own -- the owner frees it and the address range is mapped
+ * again, while the GPU mapping still points at the old pages -- is CHECKED on every call that
+ * uses such a range: four sample words of x are compared as the GPU sees them through the
+ * mapping with what the host sees, and four words of y as the GPU wrote them with what the host
+ * reads back; on a mismatch the range is unregistered for good and the call is redone through
+ * the bounce buffer.  It stays opt-in all the same: a stale registration also misleads every
+ * OTHER user of the CUDA runtime in the process (a cudaMemcpy from that address range would
+ * read the old pages), which this library cannot check; a caller whose vectors live as long
+ * as the process (the reference's Fortran and C callers) has nothing to fear.
+ * Returns true when [p, p + bytes) lies in memory registered by this library -- by this call
+ * or by an earlier one for ANY vector: a different vector that now lives where a registered one
+ * used to be is exactly the stale case -- and must therefore be checked. */
+static bool maybe_auto_pin(const void *p, size_t bytes)
+{
+    if (bytes == 0) return false;
+    if (spans_cover(p, bytes)) return true;
+    if (!g_auto_pin || spans_intersect(p, bytes)) return false;
+    char *lo = (char *)p, *hi = lo + bytes;
+    AutoPin *hit = nullptr;
+    for (AutoPin &a : g_auto)
+        if (a.lo == lo && a.hi == hi) { hit = &a; break; }
+    if (!hit) {
+        if (g_auto.size() >= 32) {                 /* forget (and release) the least recently used */
+            size_t v = 0;
+            for (size_t i = 1; i < g_auto.size(); ++i)
+                if (g_auto[i].last_use < g_auto[v].last_use) v = i;
+            g_auto[v] = g_auto.back();              /* its registration, if any, stays: spans are shared */
+            g_auto.pop_back();
+        }
+        AutoPin a = {lo, hi, 0, false, false, 0};
+        g_auto.push_back(a);
+        hit = &g_auto.back();
+    }
+    hit->last_use = g_tick;
+    if (hit->failed) return false;
+    if (hit->registered) return true;
+    if (++hit->seen < g_auto_pin) return false;
+    if (pinned_device_alias(p, bytes)) return false;        /* pinned by its owner: trusted */
+    /* Registration is page-granular and must not overlap an existing one, and callers keep
+     * their vectors side by side (NPB: x, z, p, q, r are consecutive in one COMMON block, so
+     * neighbours share a page): spans that touch are merged into one registration. */
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGE_SIZE);
+    char *slo = (char *)((uintptr_t)lo / page * page);
+    char *shi = (char *)(((uintptr_t)hi + page - 1) / page * page);
+    for (size_t i = 0; i < g_spans.size();) {
+        if (g_spans[i].lo <= shi && slo <= g_spans[i].hi) {            /* overlaps or abuts */
+            cudaHostUnregister(g_spans[i].lo);
+            cudaGetLastError();
+            slo = std::min(slo, g_spans[i].lo);
+            shi = std::max(shi, g_spans[i].hi);
+            g_spans[i] = g_spans.back();
+            g_spans.pop_back();
+            i = 0;                                                     /* the union may touch more */
+        } else {
+            ++i;
+        }
+    }
+    if (cudaHostRegister(slo, (size_t)(shi - slo), cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+        cudaGetLastError();
+        /* e.g. the span touches memory registered by somebody else: nothing of it is ours now */
+        for (AutoPin &a : g_auto)
+            if (a.registered && a.lo < shi && slo < a.hi) { a.registered = false; a.failed = true; }
+        hit->failed = true;
+        return false;
+    }
+    RegSpan sp = {slo, shi};
+    g_spans.push_back(sp);
+    hit->registered = true;
+    return true;
+}
+
+/* the mapping of an auto-registered range turned out stale: never use it (or what shares its
+ * registration) again */
+static void auto_pin_revoke(const void *p)
+{
     const char *c = (const char *)p;
-    for (const PinnedRange &r : g_pinned)
-        if (c >= r.lo && c + bytes <= r.hi) return;
-    register_range_locked((void *)p, bytes);
+    for (size_t i = 0; i < g_spans.size(); ++i) {
+        if (c < g_spans[i].lo || c >= g_spans[i].hi) continue;
+        cudaHostUnregister(g_spans[i].lo);
+        cudaGetLastError();
+        for (AutoPin &a : g_auto)
+            if (a.lo < g_spans[i].hi && g_spans[i].lo < a.hi) { a.registered = false; a.failed = true; }
+        g_spans[i] = g_spans.back();
+        g_spans.pop_back();
+        if (g_verbose) fprintf(stderr, "libb200-spmv: registered vector %p was remapped by its owner; "
+                                       "back to the bounce buffer\n", p);
+        return;
+    }
+}
+
+/* four sample positions (byte offsets, multiples of es) spread over [0, bytes) */
+static void sample_offsets(size_t bytes, size_t es, size_t off[4])
+{
+    const size_t n = bytes / es;
+    const size_t idx[4] = {0, n / 3, (2 * n) / 3, n ? n - 1 : 0};
+    for (int k = 0; k < 4; ++k) off[k] = idx[k] * es;
 }
 
 /* ------------------------------------------------------------------------
@@ -521,20 +637,27 @@ static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *co
 /* ------------------------------------------------------------------------
  * one call
  * ---------------------------------------------------------------------- */
-static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
-                           const int *colidx, const int *rows, int dtype)
+/* one product through the resident entry; false: an auto-registered vector turned out to be
+ * remapped (it has been revoked) and the call must be redone */
+static bool run_call(CacheEntry &e, void *ov, const void *iv, int n, int dtype, bool allow_auto)
 {
-    pthread_mutex_lock(&g_lock);
-    ensure_conf_locked();
-    const int n = *rows;
-    CacheEntry *ep = lookup_locked(a, rowstr, colidx, n, dtype);
-    CacheEntry &e = *ep;
-    const double t0 = now_ms();
-    if (n > 0) {
+    {
         const size_t es = elem_size(dtype);
         const size_t x_used = (size_t)e.ncols * es;
-        maybe_auto_pin(iv, e.x_bytes);
-        maybe_auto_pin(ov, e.y_bytes);
+        /* memory registered by this library is only ever used with the probes on; a range that
+         * merely touches such memory (or a redo after a failed probe) takes the bounce buffer */
+        const bool x_auto = allow_auto && x_used > 0 && maybe_auto_pin(iv, x_used);
+        const bool y_auto = allow_auto && maybe_auto_pin(ov, (size_t)n * es);
+        const bool x_avoid = !x_auto && x_used > 0 && spans_intersect(iv, x_used);
+        const bool y_avoid = !y_auto && spans_intersect(ov, (size_t)n * es);
+        size_t x_off[4] = {0, 0, 0, 0}, y_off[4] = {0, 0, 0, 0};
+        unsigned long long x_val[4] = {0, 0, 0, 0};
+        if (x_auto) {
+            sample_offsets(x_used, es, x_off);
+            for (int k = 0; k < 4; ++k) memcpy(&x_val[k], (const char *)iv + x_off[k], es);
+            g_probe->x_bad = 0;
+        }
+        if (y_auto) sample_offsets((size_t)n * es, es, y_off);
         /* x: host -> device (gpu.c:264).  Pinned caller memory is read in place over PCIe
          * by a copy kernel on the library's stream (no copy-engine hop); pageable memory
          * goes through the pinned bounce buffer first.  (Letting the product kernel fetch x
@@ -546,7 +669,7 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         const char *x_pinned = nullptr;       /* host pointer to pinned x, for the copy engine */
         const char *x_alias = nullptr;        /* its device alias, for the copy kernel */
         if (x_used > 0) {
-            x_alias = (const char *)pinned_device_alias(iv, x_used);
+            x_alias = x_avoid ? nullptr : (const char *)pinned_device_alias(iv, x_used);
             x_pinned = (const char *)iv;
             if (!x_alias) {
                 memcpy(e.h_x, iv, x_used);
@@ -557,7 +680,7 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         }
         /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
          * straight into pinned host memory (the caller's, else the bounce buffer). */
-        char *y_alias = (char *)pinned_device_alias(ov, (size_t)n * es);
+        char *y_alias = y_avoid ? nullptr : (char *)pinned_device_alias(ov, (size_t)n * es);
         const bool y_direct = y_alias != nullptr;
         char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
         if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
@@ -577,6 +700,8 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
             use(pt.ctx->device);
             cudaStream_t s = pt.ctx->stream;
             const size_t bytes = pt.x_hi - pt.x_lo;
+            if (p == 0 && x_auto)      /* what does the GPU see through the mapping we registered? */
+                launch_probe_x(x_alias, x_off, x_val, (int)es, &g_probe->x_bad, s);
             if (multi) {
                 /* one kernel: read the slice over this device's PCIe link, store it into every
                  * device's x buffer (the peers' over NVLink), then publish the call number on
@@ -600,6 +725,7 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         }
         int launched = 0;
         int timed_part = -1;
+        bool y_probed = false;
         for (int p = 0; p < e.nparts; ++p) {
             Part &pt = e.part[p];
             const int prow = pt.row_hi - pt.row_lo;
@@ -624,6 +750,10 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
             if (!y_target)
                 CUDA_OK(cudaMemcpyAsync(y_host + (size_t)pt.row_lo * es, pt.d_y, (size_t)prow * es,
                                         cudaMemcpyDeviceToHost, s));
+            if (y_auto && y_direct && pt.row_lo == 0) {  /* ... and what went back through it? */
+                launch_probe_y(y_alias, y_off, (int)es, (size_t)prow * es, g_probe->y_val, s);
+                y_probed = true;
+            }
         }
         float kernel_ms = 0.f;
         for (int p = 0; p < e.nparts; ++p)
@@ -631,11 +761,40 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
         if (timed_part >= 0)
             CUDA_OK(cudaEventElapsedTime(&kernel_ms, e.part[timed_part].ctx->ev0, e.part[timed_part].ctx->ev1));
         use(saved_dev);
+        /* an auto-registered range whose owner has remapped it: the GPU read / wrote the OLD
+         * pages.  Revoke the registration and have the call redone through the bounce buffer. */
+        bool stale = false;
+        if (x_auto && g_probe->x_bad) { auto_pin_revoke(iv); stale = true; }
+        if (y_probed) {
+            const size_t first_rows = (size_t)(e.part[0].row_hi - e.part[0].row_lo) * es;
+            for (int k = 0; k < 4 && !stale; ++k) {
+                if (y_off[k] >= first_rows) continue;       /* sampled inside the first block only */
+                unsigned long long host_view = 0;
+                memcpy(&host_view, (const char *)ov + y_off[k], es);
+                if (host_view != g_probe->y_val[k]) { auto_pin_revoke(ov); stale = true; }
+            }
+        }
+        if (stale) { g_stats.auto_pin_revoked++; return false; }
+        if (x_auto || y_auto) g_stats.auto_pinned_calls++;
         if (!y_direct) memcpy(ov, e.h_y, (size_t)n * es);
         g_stats.kernel_ms += kernel_ms;
         g_stats.kernel_launches += (uint64_t)launched;
         g_stats.h2d_bytes += x_used;
         g_stats.d2h_bytes += (size_t)n * es;
+    }
+    return true;
+}
+
+static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
+                           const int *colidx, const int *rows, int dtype)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_conf_locked();
+    const int n = *rows;
+    CacheEntry *ep = lookup_locked(a, rowstr, colidx, n, dtype);
+    const double t0 = now_ms();
+    if (n > 0 && !run_call(*ep, ov, iv, n, dtype, true)) {
+        if (!run_call(*ep, ov, iv, n, dtype, false)) die("redo through the bounce buffer failed");
     }
     g_stats.calls++;
     g_stats.e2e_ms += now_ms() - t0;
@@ -682,6 +841,19 @@ extern "C" void b200_spmv_reset_stats(void)
 {
     pthread_mutex_lock(&g_lock);
     memset(&g_stats, 0, sizeof g_stats);
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void b200_spmv_set_auto_pin(int sightings)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_conf_locked();
+    g_auto_pin = sightings > 0 ? sightings : 0;
+    if (g_auto_pin == 0) {                       /* switched off: give everything back */
+        for (const RegSpan &sp : g_spans) { cudaHostUnregister(sp.lo); cudaGetLastError(); }
+        g_spans.clear();
+        g_auto.clear();
+    }
     pthread_mutex_unlock(&g_lock);
 }
 

@@ -381,6 +381,41 @@ void launch_copy_in_multi_flagged(const void *src, void *const *dst, int ndst, s
                                                       (al & 15) == 0 ? 1 : 0, f);
 }
 
+struct ProbeArgs { size_t off[4]; unsigned long long val[4]; };
+
+__device__ __forceinline__ unsigned long long probe_word(const unsigned char *p, int es)
+{
+    return es == 8 ? *reinterpret_cast<const volatile unsigned long long *>(p)
+                   : (unsigned long long)*reinterpret_cast<const volatile unsigned int *>(p);
+}
+
+__global__ void probe_x_kernel(const unsigned char *alias, ProbeArgs a, int es, int *bad)
+{
+    if (threadIdx.x < 4 && probe_word(alias + a.off[threadIdx.x], es) != a.val[threadIdx.x]) *bad = 1;
+}
+
+__global__ void probe_y_kernel(const unsigned char *alias, ProbeArgs a, int es, size_t limit,
+                               unsigned long long *out)
+{
+    if (threadIdx.x < 4 && a.off[threadIdx.x] < limit) out[threadIdx.x] = probe_word(alias + a.off[threadIdx.x], es);
+}
+
+void launch_probe_x(const void *alias, const size_t off[4], const unsigned long long val[4], int es,
+                    int *bad, cudaStream_t s)
+{
+    ProbeArgs a;
+    for (int k = 0; k < 4; ++k) { a.off[k] = off[k]; a.val[k] = es == 8 ? val[k] : (val[k] & 0xffffffffull); }
+    probe_x_kernel<<<1, 32, 0, s>>>(static_cast<const unsigned char *>(alias), a, es, bad);
+}
+
+void launch_probe_y(const void *alias, const size_t off[4], int es, size_t limit, unsigned long long *out,
+                    cudaStream_t s)
+{
+    ProbeArgs a;
+    for (int k = 0; k < 4; ++k) { a.off[k] = off[k]; a.val[k] = 0; }
+    probe_y_kernel<<<1, 32, 0, s>>>(static_cast<const unsigned char *>(alias), a, es, limit, out);
+}
+
 __global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long epoch)
 {
     if ((int)threadIdx.x < n) {

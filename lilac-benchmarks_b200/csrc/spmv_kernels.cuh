@@ -64,6 +64,14 @@ void launch_copy_in_multi(const void *src, void *const *dst, int ndst, size_t by
 void launch_copy_in_multi_flagged(const void *src, void *const *dst, int ndst, size_t bytes,
                                   unsigned long long *const *flag, unsigned long long epoch,
                                   unsigned int *counter, cudaStream_t s);
+/* probes of a host range registered by the library on the caller's behalf (b200_dropin.cu):
+ * bad <- 1 if any of four `es`-byte words read through the device alias differs from what the
+ * host saw; out[k] <- the word at off[k] as read through the alias (words at or beyond `limit`
+ * are skipped) */
+void launch_probe_x(const void *alias, const size_t off[4], const unsigned long long val[4], int es,
+                    int *bad, cudaStream_t s);
+void launch_probe_y(const void *alias, const size_t off[4], int es, size_t limit, unsigned long long *out,
+                    cudaStream_t s);
 /* spin (one warp) until flags[i] >= epoch for all i < n: for kernels that cannot wait themselves */
 void launch_wait_flags(const unsigned long long *flags, int n, unsigned long long epoch, cudaStream_t s);
 

@@ -35,7 +35,8 @@ class NpbDeviceCsr(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("calls", c_uint64), ("uploads", c_uint64), ("kernel_launches", c_uint64),
                 ("kernel_ms", c_double), ("e2e_ms", c_double), ("upload_ms", c_double),
-                ("h2d_bytes", c_uint64), ("d2h_bytes", c_uint64)]
+                ("h2d_bytes", c_uint64), ("d2h_bytes", c_uint64),
+                ("auto_pinned_calls", c_uint64), ("auto_pin_revoked", c_uint64)]
 
 
 _lib = None
@@ -95,6 +96,8 @@ def lib():
     L.b200_spmv_get_stats.restype = None
     L.b200_spmv_reset_stats.argtypes = []
     L.b200_spmv_reset_stats.restype = None
+    L.b200_spmv_set_auto_pin.argtypes = [c_int]
+    L.b200_spmv_set_auto_pin.restype = None
     L.b200_spmv_pin_host.argtypes = [c_void_p, c_size_t]
     L.b200_spmv_pin_host.restype = c_int
     L.b200_spmv_unpin_host.argtypes = [c_void_p]

@@ -38,10 +38,11 @@ elif cls.startswith("pl"):
 elif "/" in cls:                       # "D/8": first 1/8 of the rows of class D (one rank's block)
     letter, parts = cls.split("/")
     na = npb.cg_class(letter).na
-    m = npb.NpbMatrix(letter, 0, na // int(parts))
+    m = npb.NpbDeviceMatrix(letter, 0, na // int(parts), release_vectors=False)   # assembled on the GPU
 else:
-    m = npb.NpbMatrix(cls)
-ncols = int(m.colidx.max())
+    m = npb.NpbDeviceMatrix(cls, release_vectors=False)
+on_device = isinstance(m, npb.NpbDeviceMatrix)
+ncols = npb.cg_class(cls.split("/")[0]).na if on_device else int(m.colidx.max())
 rng = np.random.default_rng(0)
 xs = [torch.from_numpy(rng.random(ncols + 2)).cuda() for _ in range(4)]
 y = torch.zeros(m.n, dtype=torch.float64, device="cuda")
@@ -83,7 +84,7 @@ for cfg_full in configs:
                 env["B200_SPMV_PANEL_NBUF"] = opt[1:]
         kernel = "panel"
     os.environ.update(env)
-    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
+    rm = m.resident(kernel=kernel) if on_device else libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
     for i in range(10):
         rm.exec(xs[i & 3], y)
     torch.cuda.synchronize()

@@ -746,3 +746,116 @@ def test_peer_exchange_forms_on_the_ring_kernel_single_rank_group(libspmv, oracl
             assert np.array_equal(y.cpu().numpy(), refs[i % 4]), i
     finally:
         sh.close()
+
+
+AUTOPIN_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+from lilac_benchmarks_b200 import libspmv, npb
+m = npb.NpbMatrix("A")
+rng = np.random.default_rng(31)
+x = rng.standard_normal(m.n + 2)
+y = np.zeros(m.n)
+for call in range(6):
+    x[:] = rng.standard_normal(m.n + 2)
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx)), call
+st = libspmv.stats()
+assert st["auto_pinned_calls"] == 4 and st["auto_pin_revoked"] == 0, st     # calls 3..6
+keep = []
+for call in range(4):                       # fresh vectors every call: bounce buffer every time
+    x2 = rng.standard_normal(m.n + 2)
+    y2 = np.zeros(m.n)
+    keep += [x2, y2]
+    libspmv.spmv_harness(y2, m.a, x2, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y2, oracle.spmv(m.a, x2, m.rowstr, m.colidx))
+assert libspmv.stats()["auto_pinned_calls"] == 4
+libspmv.lib().b200_spmv_set_auto_pin(0)     # gives the registrations back
+libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx))
+assert libspmv.stats()["auto_pinned_calls"] == 4
+print("autopin ok")
+"""
+
+
+def test_repeated_pageable_vectors_are_registered_and_stay_exact(tmp_path):
+    """B200_SPMV_PIN_HOST=3: a pageable vector that comes back at the same address is registered
+    on its third sighting and from then on read / written in place; results stay bit-identical,
+    and vectors that are new on every call (bfs: library.cc:268-279) never qualify."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "autopin.py"
+    script.write_text(AUTOPIN_SCRIPT.format(root=root))
+    proc = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B200_SPMV_PIN_HOST="3"),
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "autopin ok" in proc.stdout, proc.stdout[-3000:]
+
+
+REMAP_SCRIPT = r"""
+import ctypes, mmap, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+from lilac_benchmarks_b200 import libspmv, npb
+libc = ctypes.CDLL(None, use_errno=True)
+libc.mmap.restype = ctypes.c_void_p
+libc.mmap.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long]
+libc.munmap.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+PROT_RW, MAP_PRIVATE, MAP_ANON, MAP_FIXED = 3, 2, 0x20, 0x10
+m = npb.NpbMatrix("A")
+size = ((m.n + 2) * 8 + 4095) // 4096 * 4096
+
+def vec_at(addr):
+    buf = (ctypes.c_double * (size // 8)).from_address(addr)
+    return np.ctypeslib.as_array(buf)[: m.n + 2]
+
+ax = libc.mmap(None, size, PROT_RW, MAP_PRIVATE | MAP_ANON, -1, 0)
+ay = libc.mmap(None, size, PROT_RW, MAP_PRIVATE | MAP_ANON, -1, 0)
+rng = np.random.default_rng(5)
+x, y = vec_at(ax), vec_at(ay)[: m.n]
+for call in range(5):                                   # registered from the third call on
+    x[:] = rng.standard_normal(m.n + 2)
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx))
+assert libspmv.stats()["auto_pinned_calls"] == 3
+# the owner frees both vectors and gets the SAME addresses back with fresh pages: the GPU
+# mapping of the registration still points at the old ones
+del x, y
+for addr in (ax, ay):
+    assert libc.munmap(addr, size) == 0
+    got = libc.mmap(addr, size, PROT_RW, MAP_PRIVATE | MAP_ANON | MAP_FIXED, -1, 0)
+    assert got == addr
+x, y = vec_at(ax), vec_at(ay)[: m.n]
+for call in range(3):
+    x[:] = rng.standard_normal(m.n + 2)
+    y[:] = -7.0
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx)), call
+st = libspmv.stats()
+assert st["auto_pin_revoked"] >= 1, st
+print("remap ok", st["auto_pin_revoked"])
+"""
+
+
+def test_registered_vector_remapped_by_its_owner_is_caught(tmp_path):
+    """The hazard of registering memory one does not own: the owner unmaps it and the same
+    addresses come back with other pages.  The per-call probes (x as the GPU sees it, y as the
+    GPU wrote it, against the host's view) catch it, the registration is dropped and the call
+    redone through the bounce buffer: every result stays bit-identical."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "remap.py"
+    script.write_text(REMAP_SCRIPT.format(root=root))
+    proc = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B200_SPMV_PIN_HOST="3"),
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "remap ok" in proc.stdout, proc.stdout[-3000:]
