@@ -50,13 +50,16 @@ using namespace b200;
 /* ------------------------------------------------------------------------
  * state
  * ---------------------------------------------------------------------- */
+static const int kMaxFlags = 16;       /* >= kMaxDevices */
+
 struct Part {
     DevCtx *ctx;
     b200_matrix *m;            /* rows [row_lo, row_hi); NULL when the block is empty */
     int row_lo, row_hi;
     size_t x_lo, x_hi;         /* byte range of x this device pulls from the host */
     char *d_x, *d_y;           /* full-length x, this block's y */
-    unsigned long long *d_flags;   /* several devices: [nparts] flag[j] = call number whose slice j has landed here */
+    unsigned long long *d_flags;   /* [kMaxFlags] flag[j] = call number whose x slice j has landed here (slices: one per
+                                    * device in ABI mode, else the chunks the copy engine delivers while the product runs) */
     unsigned int *d_counter;       /* ... and the last-block counter of this device's copy kernel */
 };
 
@@ -75,6 +78,8 @@ struct CacheEntry {
     unsigned long long epoch;  /* ... and the call number the flags carry */
     void *h_x, *h_y;           /* pinned bounce buffers (portable, mapped) */
     size_t x_bytes, y_bytes;
+    int x_chunk_cols, x_nchunks;   /* one device: x goes up in this many chunks of this many columns */
+    unsigned long long *h_epoch;   /* pinned: source of the flag copies when stream memory ops are unavailable */
 };
 
 struct PinnedRange { char *lo, *hi; };
@@ -86,6 +91,12 @@ static b200_spmv_stats g_stats;
 static bool g_conf_ready = false;
 static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 1;
 static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
+/* one device: x uploaded in chunks by the copy engine WHILE the product runs (the PANEL kernels
+ * walk the columns left to right and wait per chunk) instead of in full before it */
+static int g_x_overlap = 1, g_x_chunks = 6;
+static size_t g_x_overlap_min = 256u << 10;
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWriteValue32Fn g_write_value32 = nullptr;     /* cuStreamWriteValue32, through the runtime */
 
 /* caller vectors seen by the drop-in path (B200_SPMV_PIN_HOST) */
 struct AutoPin { char *lo, *hi; int seen; bool registered; bool failed; uint64_t last_use; };
@@ -263,6 +274,23 @@ static void ensure_conf_locked(void)
     CUDA_OK(cudaHostAlloc((void **)&g_probe, sizeof(PinProbe), cudaHostAllocPortable | cudaHostAllocMapped));
     memset(g_probe, 0, sizeof(PinProbe));
     g_guard = env_int("B200_SPMV_GUARD", 1);
+    g_x_overlap = env_int("B200_SPMV_X_OVERLAP", 1);
+    {
+        /* the product spins on flags that copies issued AFTER its launch will set */
+        const char *lb = getenv("CUDA_LAUNCH_BLOCKING");
+        if (lb && atoi(lb) != 0) g_x_overlap = 0;
+    }
+    g_x_chunks = std::min(kMaxFlags, std::max(1, env_int("B200_SPMV_X_CHUNKS", 6)));
+    g_x_overlap_min = (size_t)std::max(0, env_int("B200_SPMV_X_OVERLAP_MIN_KB", 256)) << 10;
+    if (g_x_overlap && env_int("B200_SPMV_FLAG_WRITE", 1)) {
+        void *fn = nullptr;
+        enum cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_write_value32 = (StreamWriteValue32Fn)fn;
+        else
+            cudaGetLastError();
+    }
     {
         const char *v = getenv("B200_SPMV_MULTI_MIN_NNZ");
         if (v && *v) g_multi_min_nnz = atoll(v);
@@ -504,6 +532,7 @@ static void release_entry_locked(CacheEntry &e)
         Part &pt = e.part[p];
         DeviceScope scope(pt.ctx->device);
         cudaStreamSynchronize(pt.ctx->stream);
+        cudaStreamSynchronize(pt.ctx->copy_stream);
         release_locked(pt.m);
         cudaFree(pt.d_x);
         cudaFree(pt.d_y);
@@ -512,6 +541,7 @@ static void release_entry_locked(CacheEntry &e)
     }
     if (e.h_x) cudaFreeHost(e.h_x);
     if (e.h_y) cudaFreeHost(e.h_y);
+    if (e.h_epoch) cudaFreeHost(e.h_epoch);
 }
 
 static void build_entry_locked(CacheEntry &e)
@@ -551,15 +581,27 @@ static void build_entry_locked(CacheEntry &e)
         pt.x_hi = std::min(x_used, (size_t)(p + 1) * e.cols_per_part * es);
         CUDA_OK(cudaMalloc((void **)&pt.d_x, std::max<size_t>(e.x_bytes, 16)));
         CUDA_OK(cudaMalloc((void **)&pt.d_y, std::max<size_t>((size_t)(pt.row_hi - pt.row_lo) * es, 16)));
+        CUDA_OK(cudaMalloc((void **)&pt.d_flags, kMaxFlags * sizeof(unsigned long long)));
+        CUDA_OK(cudaMemsetAsync(pt.d_flags, 0, kMaxFlags * sizeof(unsigned long long), pt.ctx->stream));
         if (multi) {
-            CUDA_OK(cudaMalloc((void **)&pt.d_flags, kMaxDevices * sizeof(unsigned long long)));
-            CUDA_OK(cudaMemset(pt.d_flags, 0, kMaxDevices * sizeof(unsigned long long)));
             CUDA_OK(cudaMalloc((void **)&pt.d_counter, sizeof(unsigned int)));
-            CUDA_OK(cudaMemset(pt.d_counter, 0, sizeof(unsigned int)));
+            CUDA_OK(cudaMemsetAsync(pt.d_counter, 0, sizeof(unsigned int), pt.ctx->stream));
         }
+        /* the flags are written from other streams (and other devices) from the first call on */
+        CUDA_OK(cudaStreamSynchronize(pt.ctx->stream));
     }
     CUDA_OK(cudaHostAlloc(&e.h_x, e.x_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     CUDA_OK(cudaHostAlloc(&e.h_y, e.y_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    CUDA_OK(cudaHostAlloc((void **)&e.h_epoch, kMaxFlags * sizeof(unsigned long long), cudaHostAllocPortable));
+    memset(e.h_epoch, 0, kMaxFlags * sizeof(unsigned long long));
+    /* chunks of the overlapped upload: a multiple of 2048 columns each (whole 16-byte granules
+     * for the bulk copies of the kernels, and no chunk worth less than a copy's fixed cost) */
+    {
+        const int cg = 2048;
+        const int per = (std::max(e.ncols, 1) + g_x_chunks - 1) / g_x_chunks;
+        e.x_chunk_cols = std::max(cg, (per + cg - 1) / cg * cg);
+        e.x_nchunks = (std::max(e.ncols, 1) + e.x_chunk_cols - 1) / e.x_chunk_cols;
+    }
     if (g_verbose && multi) {
         fprintf(stderr, "libb200-spmv: matrix rows=%d nnz=%lld spread over %d devices:", e.rows,
                 (long long)e.nnz, e.nparts);
@@ -570,24 +612,42 @@ static void build_entry_locked(CacheEntry &e)
     }
 }
 
+/* the content checks of a cache hit (probes + one rolling window): ~10 us of host time on a
+ * large matrix, so the caller runs them AFTER the launches, while the GPU works, and redoes
+ * the call when they fail */
+static bool entry_content_stale(CacheEntry &e)
+{
+    const size_t es = elem_size(e.dtype);
+    bool stale = fingerprint(e.a, e.rowstr, e.colidx, e.rows, e.nnz, es) != e.fingerprint;
+    if (!stale && !e.win_hash.empty()) {
+        stale = window_hash(e, e.win_next) != e.win_hash[e.win_next];
+        e.win_next = (e.win_next + 1) % e.win_hash.size();
+    }
+    return stale;
+}
+
+static void drop_entry_locked(CacheEntry *ep)
+{
+    const size_t i = (size_t)(ep - g_cache.data());
+    if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
+    release_entry_locked(g_cache[i]);
+    g_cache[i] = g_cache.back();
+    g_cache.pop_back();
+}
+
+/* *unchecked: the entry is a cache hit whose content checks are still to be run */
 static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *colidx,
-                                 int rows, int dtype)
+                                 int rows, int dtype, bool *unchecked)
 {
     const int64_t nnz = rows > 0 ? (int64_t)rowstr[rows] - rowstr[0] : 0;
     const size_t es = elem_size(dtype);
     ++g_tick;
+    *unchecked = false;
     for (size_t i = 0; i < g_cache.size(); ++i) {
         CacheEntry &e = g_cache[i];
         if (e.a == a && e.rowstr == rowstr && e.colidx == colidx && e.rows == rows &&
             e.nnz == nnz && e.dtype == dtype) {
-            bool stale = e.guard_slot >= 0 && g_guards[e.guard_slot].tripped;
-            if (!stale && g_validate) {
-                stale = fingerprint(a, rowstr, colidx, rows, nnz, es) != e.fingerprint;
-                if (!stale && !e.win_hash.empty()) {
-                    stale = window_hash(e, e.win_next) != e.win_hash[e.win_next];
-                    e.win_next = (e.win_next + 1) % e.win_hash.size();
-                }
-            }
+            const bool stale = e.guard_slot >= 0 && g_guards[e.guard_slot].tripped;
             if (stale) {
                 if (g_verbose) fprintf(stderr, "libb200-spmv: host matrix changed, re-uploading\n");
                 release_entry_locked(e);
@@ -596,6 +656,7 @@ static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *co
                 break;
             }
             e.last_use = g_tick;
+            *unchecked = g_validate != 0;
             return &e;
         }
     }
@@ -616,6 +677,7 @@ static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *co
     e.guard_slot = -1;
     e.win_next = 0;
     e.h_x = e.h_y = nullptr;
+    e.h_epoch = nullptr;
     build_entry_locked(e);
     if (g_validate) {
         e.fingerprint = fingerprint(a, rowstr, colidx, rows, nnz, es);
@@ -637,152 +699,210 @@ static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *co
 /* ------------------------------------------------------------------------
  * one call
  * ---------------------------------------------------------------------- */
-/* one product through the resident entry; false: an auto-registered vector turned out to be
- * remapped (it has been revoked) and the call must be redone */
-static bool run_call(CacheEntry &e, void *ov, const void *iv, int n, int dtype, bool allow_auto)
-{
-    {
-        const size_t es = elem_size(dtype);
-        const size_t x_used = (size_t)e.ncols * es;
-        /* memory registered by this library is only ever used with the probes on; a range that
-         * merely touches such memory (or a redo after a failed probe) takes the bounce buffer */
-        const bool x_auto = allow_auto && x_used > 0 && maybe_auto_pin(iv, x_used);
-        const bool y_auto = allow_auto && maybe_auto_pin(ov, (size_t)n * es);
-        const bool x_avoid = !x_auto && x_used > 0 && spans_intersect(iv, x_used);
-        const bool y_avoid = !y_auto && spans_intersect(ov, (size_t)n * es);
-        size_t x_off[4] = {0, 0, 0, 0}, y_off[4] = {0, 0, 0, 0};
-        unsigned long long x_val[4] = {0, 0, 0, 0};
-        if (x_auto) {
-            sample_offsets(x_used, es, x_off);
-            for (int k = 0; k < 4; ++k) memcpy(&x_val[k], (const char *)iv + x_off[k], es);
-            g_probe->x_bad = 0;
-        }
-        if (y_auto) sample_offsets((size_t)n * es, es, y_off);
-        /* x: host -> device (gpu.c:264).  Pinned caller memory is read in place over PCIe
-         * by a copy kernel on the library's stream (no copy-engine hop); pageable memory
-         * goes through the pinned bounce buffer first.  (Letting the product kernel fetch x
-         * itself, chunk by chunk behind flags, so that the transfer overlaps the matrix stream,
-         * was built and measured: a GPU-issued PCIe read takes ~10 us to come back, a window
-         * of chunks in flight serialises on that, and without a window the chunks do not land
-         * in column order -- 208 us per call against 157 us; the fetch state also cost the
-         * class C kernel 10 % at its 128-register limit.  profiles/r02_run13_bench_C*.json) */
-        const char *x_pinned = nullptr;       /* host pointer to pinned x, for the copy engine */
-        const char *x_alias = nullptr;        /* its device alias, for the copy kernel */
-        if (x_used > 0) {
-            x_alias = x_avoid ? nullptr : (const char *)pinned_device_alias(iv, x_used);
-            x_pinned = (const char *)iv;
-            if (!x_alias) {
-                memcpy(e.h_x, iv, x_used);
-                x_pinned = (const char *)e.h_x;
-                x_alias = (const char *)pinned_device_alias(e.h_x, x_used);
-                if (!x_alias) die("the pinned bounce buffer has no device alias");
-            }
-        }
-        /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
-         * straight into pinned host memory (the caller's, else the bounce buffer). */
-        char *y_alias = y_avoid ? nullptr : (char *)pinned_device_alias(ov, (size_t)n * es);
-        const bool y_direct = y_alias != nullptr;
-        char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
-        if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
+enum CallResult {
+    CALL_OK = 0,
+    CALL_REDO_BOUNCE,      /* an auto-registered vector turned out to be remapped (revoked): redo without it */
+    CALL_STALE_MATRIX      /* the content checks failed: the resident copy is out of date, re-upload and redo */
+};
 
-        const bool multi = e.nparts > 1;
-        /* one cudaSetDevice per device and loop, restored once at the end: with eight devices
-         * the host side of a call is a few dozen runtime calls, and it is the critical path
-         * (the first version -- a device scope per step, an event per slice and 56 stream
-         * waits -- spent 0.24 ms of a 0.51 ms call in the runtime) */
-        int saved_dev = -1, cur_dev = -1;
-        cudaGetDevice(&saved_dev);
-        cur_dev = saved_dev;
-        auto use = [&](int d) { if (d != cur_dev) { CUDA_OK(cudaSetDevice(d)); cur_dev = d; } };
-        const unsigned long long epoch = ++e.epoch;
-        for (int p = 0; p < e.nparts; ++p) {
-            Part &pt = e.part[p];
-            use(pt.ctx->device);
-            cudaStream_t s = pt.ctx->stream;
-            const size_t bytes = pt.x_hi - pt.x_lo;
-            if (p == 0 && x_auto)      /* what does the GPU see through the mapping we registered? */
-                launch_probe_x(x_alias, x_off, x_val, (int)es, &g_probe->x_bad, s);
-            if (multi) {
-                /* one kernel: read the slice over this device's PCIe link, store it into every
-                 * device's x buffer (the peers' over NVLink), then publish the call number on
-                 * every device's flag for this slice -- the products wait on flags, not events */
-                void *dst[kMaxDevices];
-                unsigned long long *flag[kMaxDevices];
-                for (int j = 0; j < e.nparts; ++j) {
-                    dst[j] = e.part[j].d_x + pt.x_lo;
-                    flag[j] = e.part[j].d_flags + p;
-                }
-                launch_copy_in_multi_flagged(x_alias ? x_alias + pt.x_lo : nullptr, dst, e.nparts, bytes, flag,
-                                             epoch, pt.d_counter, s);
-            } else if (bytes > 0) {
-                if (g_zero_copy) {
-                    void *dst[1] = {pt.d_x + pt.x_lo};
-                    launch_copy_in_multi(x_alias + pt.x_lo, dst, 1, bytes, s);
-                } else {
-                    CUDA_OK(cudaMemcpyAsync(pt.d_x + pt.x_lo, x_pinned + pt.x_lo, bytes, cudaMemcpyHostToDevice, s));
-                }
-            }
-        }
-        int launched = 0;
-        int timed_part = -1;
-        bool y_probed = false;
-        for (int p = 0; p < e.nparts; ++p) {
-            Part &pt = e.part[p];
-            const int prow = pt.row_hi - pt.row_lo;
-            if (!pt.m || prow <= 0) continue;
-            use(pt.ctx->device);
-            cudaStream_t s = pt.ctx->stream;
-            /* kernel timing: every call on one device; on several, the first block only */
-            const bool timed = g_time_kernels && timed_part < 0;
-            if (timed) { CUDA_OK(cudaEventRecord(pt.ctx->ev0, s)); timed_part = p; }
-            char *y_target = nullptr;
-            if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
-                y_target = y_alias + (size_t)pt.row_lo * es;
-            if (multi && exec_waits_in_kernel(pt.m)) {
-                /* the ring kernel waits per slice, just before the panels that need it */
-                SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts};
-                launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
-            } else {
-                if (multi) launch_wait_flags(pt.d_flags, e.nparts, epoch, s);
-                launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, nullptr);
-            }
-            if (timed) CUDA_OK(cudaEventRecord(pt.ctx->ev1, s));
-            if (!y_target)
-                CUDA_OK(cudaMemcpyAsync(y_host + (size_t)pt.row_lo * es, pt.d_y, (size_t)prow * es,
-                                        cudaMemcpyDeviceToHost, s));
-            if (y_auto && y_direct && pt.row_lo == 0) {  /* ... and what went back through it? */
-                launch_probe_y(y_alias, y_off, (int)es, (size_t)prow * es, g_probe->y_val, s);
-                y_probed = true;
-            }
-        }
-        float kernel_ms = 0.f;
-        for (int p = 0; p < e.nparts; ++p)
-            CUDA_OK(cudaStreamSynchronize(e.part[p].ctx->stream));
-        if (timed_part >= 0)
-            CUDA_OK(cudaEventElapsedTime(&kernel_ms, e.part[timed_part].ctx->ev0, e.part[timed_part].ctx->ev1));
-        use(saved_dev);
-        /* an auto-registered range whose owner has remapped it: the GPU read / wrote the OLD
-         * pages.  Revoke the registration and have the call redone through the bounce buffer. */
-        bool stale = false;
-        if (x_auto && g_probe->x_bad) { auto_pin_revoke(iv); stale = true; }
-        if (y_probed) {
-            const size_t first_rows = (size_t)(e.part[0].row_hi - e.part[0].row_lo) * es;
-            for (int k = 0; k < 4 && !stale; ++k) {
-                if (y_off[k] >= first_rows) continue;       /* sampled inside the first block only */
-                unsigned long long host_view = 0;
-                memcpy(&host_view, (const char *)ov + y_off[k], es);
-                if (host_view != g_probe->y_val[k]) { auto_pin_revoke(ov); stale = true; }
-            }
-        }
-        if (stale) { g_stats.auto_pin_revoked++; return false; }
-        if (x_auto || y_auto) g_stats.auto_pinned_calls++;
-        if (!y_direct) memcpy(ov, e.h_y, (size_t)n * es);
-        g_stats.kernel_ms += kernel_ms;
-        g_stats.kernel_launches += (uint64_t)launched;
-        g_stats.h2d_bytes += x_used;
-        g_stats.d2h_bytes += (size_t)n * es;
+/* "slice k of x has landed": the call number into d_flag, ordered after the copies issued on
+ * `s` before it.  A stream memory operation when the driver has them, else an 8-byte copy. */
+static void write_flag(cudaStream_t s, unsigned long long *d_flag, unsigned long long epoch,
+                       unsigned long long *h_word)
+{
+    if (g_write_value32) {
+        /* flags are 64-bit, little endian; call numbers stay below 2^32 (run_call resets them) */
+        if (g_write_value32(s, (unsigned long long)(uintptr_t)d_flag, (unsigned int)epoch, 0u) == 0) return;
+        g_write_value32 = nullptr;                  /* not on this driver / device: copies from now on */
     }
-    return true;
+    *h_word = epoch;
+    CUDA_OK(cudaMemcpyAsync(d_flag, h_word, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+}
+
+/* one product through the resident entry.  check_content: run the staleness checks of a cache
+ * hit between the launches and the synchronisation */
+static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int dtype, bool allow_auto,
+                           bool check_content)
+{
+    const size_t es = elem_size(dtype);
+    const size_t x_used = (size_t)e.ncols * es;
+    /* memory registered by this library is only ever used with the probes on; a range that
+     * merely touches such memory (or a redo after a failed probe) takes the bounce buffer */
+    const bool x_auto = allow_auto && x_used > 0 && maybe_auto_pin(iv, x_used);
+    const bool y_auto = allow_auto && maybe_auto_pin(ov, (size_t)n * es);
+    const bool x_avoid = !x_auto && x_used > 0 && spans_intersect(iv, x_used);
+    const bool y_avoid = !y_auto && spans_intersect(ov, (size_t)n * es);
+    size_t x_off[4] = {0, 0, 0, 0}, y_off[4] = {0, 0, 0, 0};
+    unsigned long long x_val[4] = {0, 0, 0, 0};
+    if (x_auto) {
+        sample_offsets(x_used, es, x_off);
+        for (int k = 0; k < 4; ++k) memcpy(&x_val[k], (const char *)iv + x_off[k], es);
+        g_probe->x_bad = 0;
+    }
+    if (y_auto) sample_offsets((size_t)n * es, es, y_off);
+
+    const bool multi = e.nparts > 1;
+    /* One device and a kernel that walks the columns left to right (PANEL, RING): x goes up in
+     * chunks through the copy engine on a second stream WHILE the product runs; the kernel
+     * waits per chunk just before the panels that need it (XFlags).  The first chunk is issued
+     * before the launch, the others after it, so the product starts ~10 us into the call
+     * instead of after the whole vector has crossed PCIe -- and for a pageable vector the
+     * memcpy into the bounce buffer overlaps the product chunk by chunk as well.
+     * (The other way round -- the product kernel fetching x itself over PCIe, chunk by chunk
+     * behind flags -- was built and measured: a GPU-issued PCIe read takes ~10 us to come
+     * back, a window of chunks in flight serialises on that, and without a window the chunks
+     * do not land in column order: 208 us per call against 157 us, profiles/r02_run13_bench_C*.json.) */
+    const bool overlap = !multi && g_x_overlap && x_used >= g_x_overlap_min && x_used > 0 &&
+                         e.part[0].m && exec_takes_flags(e.part[0].m) && e.x_nchunks <= kMaxFlags;
+
+    /* x: host -> device (gpu.c:264).  Without the overlap, pinned caller memory is read in
+     * place over PCIe by a copy kernel on the library's stream; pageable memory goes through
+     * the pinned bounce buffer first. */
+    const char *x_pinned = nullptr;       /* host pointer to pinned x, for the copy engine */
+    const char *x_alias = nullptr;        /* its device alias, for the copy kernel */
+    bool x_bounce = false;
+    if (x_used > 0) {
+        x_alias = x_avoid ? nullptr : (const char *)pinned_device_alias(iv, x_used);
+        x_pinned = (const char *)iv;
+        if (!x_alias) {
+            x_bounce = true;
+            if (!overlap) memcpy(e.h_x, iv, x_used);
+            x_pinned = (const char *)e.h_x;
+            x_alias = (const char *)pinned_device_alias(e.h_x, x_used);
+            if (!x_alias) die("the pinned bounce buffer has no device alias");
+        }
+    }
+    /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
+     * straight into pinned host memory (the caller's, else the bounce buffer). */
+    char *y_alias = y_avoid ? nullptr : (char *)pinned_device_alias(ov, (size_t)n * es);
+    const bool y_direct = y_alias != nullptr;
+    char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
+    if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
+
+    /* one cudaSetDevice per device and loop, restored once at the end: with eight devices
+     * the host side of a call is a few dozen runtime calls, and it is the critical path
+     * (the first version -- a device scope per step, an event per slice and 56 stream
+     * waits -- spent 0.24 ms of a 0.51 ms call in the runtime) */
+    int saved_dev = -1, cur_dev = -1;
+    cudaGetDevice(&saved_dev);
+    cur_dev = saved_dev;
+    auto use = [&](int d) { if (d != cur_dev) { CUDA_OK(cudaSetDevice(d)); cur_dev = d; } };
+    if (overlap && e.epoch >= 0xFFFFFFF0ull) {        /* 32-bit flag writes: start the call numbers over */
+        use(e.part[0].ctx->device);
+        CUDA_OK(cudaMemsetAsync(e.part[0].d_flags, 0, kMaxFlags * sizeof(unsigned long long), e.part[0].ctx->stream));
+        CUDA_OK(cudaStreamSynchronize(e.part[0].ctx->stream));
+        e.epoch = 0;
+    }
+    const unsigned long long epoch = ++e.epoch;
+    /* chunk k of the overlapped upload: (memcpy into the bounce buffer,) copy, flag */
+    auto send_chunk = [&](int k) {
+        Part &pt = e.part[0];
+        const size_t lo = std::min(x_used, (size_t)k * e.x_chunk_cols * es);
+        const size_t hi = std::min(x_used, (size_t)(k + 1) * e.x_chunk_cols * es);
+        if (hi > lo) {
+            if (x_bounce) memcpy((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
+            CUDA_OK(cudaMemcpyAsync(pt.d_x + lo, x_pinned + lo, hi - lo, cudaMemcpyHostToDevice, pt.ctx->copy_stream));
+        }
+        write_flag(pt.ctx->copy_stream, pt.d_flags + k, epoch, e.h_epoch + k);
+    };
+    for (int p = 0; p < e.nparts; ++p) {
+        Part &pt = e.part[p];
+        use(pt.ctx->device);
+        cudaStream_t s = pt.ctx->stream;
+        const size_t bytes = pt.x_hi - pt.x_lo;
+        if (p == 0 && x_auto)      /* what does the GPU see through the mapping we registered? */
+            launch_probe_x(x_alias, x_off, x_val, (int)es, &g_probe->x_bad, s);
+        if (multi) {
+            /* one kernel: read the slice over this device's PCIe link, store it into every
+             * device's x buffer (the peers' over NVLink), then publish the call number on
+             * every device's flag for this slice -- the products wait on flags, not events */
+            void *dst[kMaxDevices];
+            unsigned long long *flag[kMaxDevices];
+            for (int j = 0; j < e.nparts; ++j) {
+                dst[j] = e.part[j].d_x + pt.x_lo;
+                flag[j] = e.part[j].d_flags + p;
+            }
+            launch_copy_in_multi_flagged(x_alias ? x_alias + pt.x_lo : nullptr, dst, e.nparts, bytes, flag,
+                                         epoch, pt.d_counter, s);
+        } else if (overlap) {
+            send_chunk(0);
+        } else if (bytes > 0) {
+            if (g_zero_copy) {
+                void *dst[1] = {pt.d_x + pt.x_lo};
+                launch_copy_in_multi(x_alias + pt.x_lo, dst, 1, bytes, s);
+            } else {
+                CUDA_OK(cudaMemcpyAsync(pt.d_x + pt.x_lo, x_pinned + pt.x_lo, bytes, cudaMemcpyHostToDevice, s));
+            }
+        }
+    }
+    int launched = 0;
+    int timed_part = -1;
+    bool y_probed = false;
+    for (int p = 0; p < e.nparts; ++p) {
+        Part &pt = e.part[p];
+        const int prow = pt.row_hi - pt.row_lo;
+        if (!pt.m || prow <= 0) continue;
+        use(pt.ctx->device);
+        cudaStream_t s = pt.ctx->stream;
+        /* kernel timing: every call on one device; on several, the first block only */
+        const bool timed = g_time_kernels && timed_part < 0;
+        if (timed) { CUDA_OK(cudaEventRecord(pt.ctx->ev0, s)); timed_part = p; }
+        char *y_target = nullptr;
+        if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
+            y_target = y_alias + (size_t)pt.row_lo * es;
+        if (overlap) {
+            SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks};
+            launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
+        } else if (multi && exec_waits_in_kernel(pt.m)) {
+            /* the ring kernel waits per slice, just before the panels that need it */
+            SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts};
+            launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
+        } else {
+            if (multi) launch_wait_flags(pt.d_flags, e.nparts, epoch, s);
+            launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, nullptr);
+        }
+        if (timed) CUDA_OK(cudaEventRecord(pt.ctx->ev1, s));
+        if (!y_target)
+            CUDA_OK(cudaMemcpyAsync(y_host + (size_t)pt.row_lo * es, pt.d_y, (size_t)prow * es,
+                                    cudaMemcpyDeviceToHost, s));
+        if (y_auto && y_direct && pt.row_lo == 0) {  /* ... and what went back through it? */
+            launch_probe_y(y_alias, y_off, (int)es, (size_t)prow * es, g_probe->y_val, s);
+            y_probed = true;
+        }
+    }
+    if (overlap)                                   /* the rest of x follows the launch */
+        for (int k = 1; k < e.x_nchunks; ++k) send_chunk(k);
+    /* the GPU is busy: now the content checks of the cache hit */
+    const bool matrix_stale = check_content && entry_content_stale(e);
+    float kernel_ms = 0.f;
+    for (int p = 0; p < e.nparts; ++p)
+        CUDA_OK(cudaStreamSynchronize(e.part[p].ctx->stream));
+    if (overlap) CUDA_OK(cudaStreamSynchronize(e.part[0].ctx->copy_stream));
+    if (timed_part >= 0)
+        CUDA_OK(cudaEventElapsedTime(&kernel_ms, e.part[timed_part].ctx->ev0, e.part[timed_part].ctx->ev1));
+    use(saved_dev);
+    if (matrix_stale) return CALL_STALE_MATRIX;
+    /* an auto-registered range whose owner has remapped it: the GPU read / wrote the OLD
+     * pages.  Revoke the registration and have the call redone through the bounce buffer. */
+    bool stale = false;
+    if (x_auto && g_probe->x_bad) { auto_pin_revoke(iv); stale = true; }
+    if (y_probed) {
+        const size_t first_rows = (size_t)(e.part[0].row_hi - e.part[0].row_lo) * es;
+        for (int k = 0; k < 4 && !stale; ++k) {
+            if (y_off[k] >= first_rows) continue;       /* sampled inside the first block only */
+            unsigned long long host_view = 0;
+            memcpy(&host_view, (const char *)ov + y_off[k], es);
+            if (host_view != g_probe->y_val[k]) { auto_pin_revoke(ov); stale = true; }
+        }
+    }
+    if (stale) { g_stats.auto_pin_revoked++; return CALL_REDO_BOUNCE; }
+    if (x_auto || y_auto) g_stats.auto_pinned_calls++;
+    if (!y_direct) memcpy(ov, e.h_y, (size_t)n * es);
+    g_stats.kernel_ms += kernel_ms;
+    g_stats.kernel_launches += (uint64_t)launched;
+    g_stats.h2d_bytes += x_used;
+    g_stats.d2h_bytes += (size_t)n * es;
+    return CALL_OK;
 }
 
 static void harness_common(void *ov, const void *a, const void *iv, const int *rowstr,
@@ -791,10 +911,24 @@ static void harness_common(void *ov, const void *a, const void *iv, const int *r
     pthread_mutex_lock(&g_lock);
     ensure_conf_locked();
     const int n = *rows;
-    CacheEntry *ep = lookup_locked(a, rowstr, colidx, n, dtype);
+    bool unchecked = false;
+    CacheEntry *ep = lookup_locked(a, rowstr, colidx, n, dtype, &unchecked);
     const double t0 = now_ms();
-    if (n > 0 && !run_call(*ep, ov, iv, n, dtype, true)) {
-        if (!run_call(*ep, ov, iv, n, dtype, false)) die("redo through the bounce buffer failed");
+    if (n > 0) {
+        bool allow_auto = true;
+        for (int attempt = 0; ; ++attempt) {
+            const CallResult r = run_call(*ep, ov, iv, n, dtype, allow_auto, unchecked);
+            if (r == CALL_OK) break;
+            if (attempt >= 3) die("the call could not be completed (result %d)", (int)r);
+            if (r == CALL_REDO_BOUNCE) allow_auto = false;
+            if (r == CALL_STALE_MATRIX) {               /* the product ran on the old copy: upload, redo */
+                drop_entry_locked(ep);
+                ep = lookup_locked(a, rowstr, colidx, n, dtype, &unchecked);
+            }
+        }
+    } else if (unchecked && entry_content_stale(*ep)) {
+        drop_entry_locked(ep);
+        ep = lookup_locked(a, rowstr, colidx, n, dtype, &unchecked);
     }
     g_stats.calls++;
     g_stats.e2e_ms += now_ms() - t0;

@@ -106,6 +106,7 @@ DevCtx *ctx_for_device_locked(int device)
     c->device = device;
     CUDA_OK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&c->ev0));
     CUDA_OK(cudaEventCreate(&c->ev1));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
@@ -747,6 +748,11 @@ bool exec_waits_in_kernel(const b200_matrix *m)
     return m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 2;
 }
 
+bool exec_takes_flags(const b200_matrix *m)
+{
+    return m->kernel == B200_KERNEL_PANEL && (m->panel.fmt == 2 || m->panel.fmt == 0);
+}
+
 int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
                 const XPush *xp)
 {
@@ -763,10 +769,16 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
                 launch_panelr<double>(m->panel, (const double *)d_x, (double *)d_y, xf, push, s);
             else
                 launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, push, s);
-        } else if (m->dtype == B200_F64)
-            launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s);
-        else
-            launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s);
+        } else {
+            XFlags xf = {nullptr, 0ull, 1, 0};
+            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks; }
+            if (m->dtype == B200_F64)
+                launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s, nullptr, nullptr,
+                                     xf.flags ? &xf : nullptr);
+            else
+                launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s, nullptr, nullptr,
+                                    xf.flags ? &xf : nullptr);
+        }
     } else if (m->kernel == B200_KERNEL_SELL || m->kernel == B200_KERNEL_MERGE) {
         if (m->dtype == B200_F64)
             launch_sell<double>(m->sell, m->dev, (const double *)d_x, (double *)d_y, s);
@@ -852,7 +864,7 @@ extern "C" int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y,
                                      int cols_per_rank, int nranks)
 {
     if (!m) die("b200_spmv_exec_sliced: null matrix");
-    if (!exec_waits_in_kernel(m)) return -1;
+    if (!exec_takes_flags(m)) return -1;
     DeviceScope scope(m->device);
     SliceFlags sf = {flags, epoch, cols_per_rank, nranks};
     return exec_locked(m, d_x, d_y, (cudaStream_t)stream, &sf);

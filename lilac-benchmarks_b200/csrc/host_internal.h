@@ -40,6 +40,7 @@ struct DevCtx {
     int device;
     int sm_count;
     cudaStream_t stream;          /* non-blocking; uploads and the drop-in path run here */
+    cudaStream_t copy_stream;     /* drop-in path: x chunks host -> device (copy engine) while the product runs */
     cudaEvent_t ev0, ev1;         /* kernel timing of the drop-in path */
     cudaEvent_t ev_x;             /* multi-device: "my x slice is in every device's buffer" */
 };
@@ -104,9 +105,10 @@ b200_matrix *upload_locked(DevCtx *ctx, const void *a, const int *rowstr, const 
 void release_locked(b200_matrix *m);
 /* launches on `s` (a stream of m->device, which must be current); returns the number of
  * kernels launched.  `sf` != NULL: the kernel itself waits for the x slices (only the
- * RING kernel can; for the others the caller must have waited -- see exec_waits_in_kernel) */
+ * PANEL kernels can -- exec_takes_flags; for the others the caller must have waited) */
 int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
                 const XPush *xp = nullptr);
-bool exec_waits_in_kernel(const b200_matrix *m);
+bool exec_takes_flags(const b200_matrix *m);        /* paired PANEL and RING kernels */
+bool exec_waits_in_kernel(const b200_matrix *m);    /* RING kernel: flags and the fused push (multi-GPU paths) */
 
 }  // namespace b200

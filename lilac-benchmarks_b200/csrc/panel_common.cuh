@@ -68,6 +68,21 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsign
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/* x that arrives slice by slice (XFlags: from other GPUs over NVLink, or from the host through
+ * the copy engine while the product runs): before a panel's x slice is requested, the slices
+ * holding its columns [cbase, cbase + cw) must have landed.  Columns are walked left to right,
+ * so `ready` (slices [0, ready) have arrived) only grows.  One thread calls this. */
+__device__ __forceinline__ void wait_x_slices(const XFlags &xf, int &ready, int cbase, int cw)
+{
+    const int r1 = min((cbase + cw - 1) / xf.cols_per_rank, xf.nranks - 1);
+    if (r1 < ready) return;
+    for (; ready <= r1; ++ready)
+        while (ld_acquire_sys_u64(xf.flags + ready) < xf.epoch) { }
+    /* the slice was written through the generic proxy (another GPU) or by a copy engine, the
+     * bulk copy reads it through the async proxy */
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 /* host side: true when the calling device has been seen before (bit per device ordinal);
  * used to set function attributes once per device (callers hold the library lock, or
  * race benignly: setting an attribute twice is harmless) */

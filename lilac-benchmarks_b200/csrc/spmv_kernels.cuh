@@ -112,9 +112,11 @@ void launch_panel_fill(const T *val, const int *col, const int *rowptr, int rows
                        cudaStream_t s);
 /* y = A x on the panel layout; every row summed left to right.  dotv != NULL: CTA b also
  * writes its share of dotv . y to dot_partial[b] (nblk values, fixed reduction order) */
+struct XFlags;
+/* flags != NULL: x arrives chunk by chunk while the kernel runs, see XFlags below */
 template <typename T>
 void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T *dotv = nullptr,
-                  T *dot_partial = nullptr);
+                  T *dot_partial = nullptr, const XFlags *flags = nullptr);
 size_t panel_smem_bytes(const DevPanel &pm, bool f32);
 
 /* flagged-stream layout for wide matrices: build passes (spmv_panelg.cu) */

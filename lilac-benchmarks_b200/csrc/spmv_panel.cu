@@ -241,13 +241,13 @@ __device__ __forceinline__ T consume_chunk(const Chunk<T, U> &ch, const T *xs, T
     return acc;
 }
 
-template <typename T, int U, int MAXT>
+template <typename T, int U, int MAXT, bool XF>
 __global__ void __launch_bounds__(MAXT, 1)
 spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
                   const ushort4 *__restrict__ meta, const int *__restrict__ slice_off,
                   const T *__restrict__ x, T *__restrict__ y,
                   int rows, int ncols, int P, int W, int R, int use_tma, int nbuf,
-                  const T *__restrict__ dotv, T *__restrict__ dot_partial)
+                  const T *__restrict__ dotv, T *__restrict__ dot_partial, XFlags xf)
 {
     using P2 = typename PairT<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -285,14 +285,21 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     ushort4 mt_next = meta[(size_t)rb * P * Tn + tid];
     __syncthreads();
 
+    /* x still on its way from the host (drop-in path: the copy engine delivers it chunk by
+     * chunk while the product runs) or from other GPUs: wait for the chunks a panel needs
+     * just before the panel is requested.  XF is a template parameter: the kernel a caller
+     * with x resident in HBM gets (XF = false) carries none of this state -- the class C
+     * instance sits at its 128-register limit */
+    int x_ready = 0;
     auto issue_panel = [&](int p) {                       /* called by thread 0 only (TMA path) */
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
         constexpr int VE = 16 / sizeof(T);
         const int cw_al = cw & ~(VE - 1);
+        if (XF) wait_x_slices(xf, x_ready, cbase, cw);
         if (cw_al < cw) {                                 /* ragged tail: generic stores, then the fence */
-            for (int i = cw_al; i < cw; ++i) dst[i] = __ldg(x + cbase + i);
+            for (int i = cw_al; i < cw; ++i) dst[i] = XF ? __ldcg(x + cbase + i) : __ldg(x + cbase + i);
             fence_proxy_async();
         }
         uint64_t *bar = &bars[p & (nbuf - 1)];
@@ -315,7 +322,13 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
         T *dst = xbuf + (size_t)(p & (nbuf - 1)) * WS;
-        for (int i = tid; i < cw; i += Tn) dst[i] = __ldg(x + cbase + i);
+        if constexpr (XF) {                               /* block-uniform */
+            if (tid == 0) wait_x_slices(xf, x_ready, cbase, cw);
+            __syncthreads();
+            for (int i = tid; i < cw; i += Tn) dst[i] = __ldcg(x + cbase + i);
+        } else {
+            for (int i = tid; i < cw; i += Tn) dst[i] = __ldg(x + cbase + i);
+        }
     };
 
     if (use_tma) {
@@ -410,40 +423,54 @@ size_t panel_smem_bytes(const DevPanel &pm, bool f32)
     return xoff + (size_t)pm.nbuf * ws * es;
 }
 
-template <typename T, int U, int MAXT>
-static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, const T *dotv, T *dot_partial, cudaStream_t s)
+template <typename T, int U, int MAXT, bool XF>
+static void launch_panel_xf(const DevPanel &pm, const T *x, T *y, const T *dotv, T *dot_partial,
+                            const XFlags &xf, cudaStream_t s)
 {
     static unsigned attr_set = 0;                  /* function attributes are per device */
     if (!attr_done(&attr_set))
-        cudaFuncSetAttribute(spmv_panel_kernel<T, U, MAXT>,
+        cudaFuncSetAttribute(spmv_panel_kernel<T, U, MAXT, XF>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const size_t smem = panel_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
-    spmv_panel_kernel<T, U, MAXT><<<pm.nblk, pm.R / pm.G, smem, s>>>(
+    spmv_panel_kernel<T, U, MAXT, XF><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const T *>(pm.val), pm.col, pm.meta, pm.slice_off, x, y,
-        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, dotv, dot_partial);
+        pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, dotv, dot_partial, xf);
+}
+
+template <typename T, int U, int MAXT>
+static void launch_panel_cfg(const DevPanel &pm, const T *x, T *y, const T *dotv, T *dot_partial,
+                             const XFlags &xf, cudaStream_t s)
+{
+    if (xf.flags) launch_panel_xf<T, U, MAXT, true>(pm, x, y, dotv, dot_partial, xf, s);
+    else          launch_panel_xf<T, U, MAXT, false>(pm, x, y, dotv, dot_partial, xf, s);
 }
 
 template <typename T>
-void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T *dotv, T *dot_partial)
+void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T *dotv, T *dot_partial,
+                  const XFlags *flags)
 {
     if (pm.nblk <= 0) return;
+    const XFlags none = {nullptr, 0ull, 1, 0};
+    const XFlags &xf = flags ? *flags : none;
     const int threads = pm.R / pm.G;
     if (threads <= 256 && pm.U >= 5) {
         /* few warps per SM (NPB class A / B sized row blocks): the register file
          * is free, so each lane keeps twice as many pairs of the stream in flight (12 pairs
          * per chunk spill and are no faster: profiles/r02_run6_sweep.txt) */
-        if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, dotv, dot_partial, s);
-        else launch_panel_cfg<T, 8, 256>(pm, x, y, dotv, dot_partial, s);     /* best on class B (profiles/r01_run23) */
+        if (pm.U >= 10) launch_panel_cfg<T, 10, 256>(pm, x, y, dotv, dot_partial, xf, s);
+        else launch_panel_cfg<T, 8, 256>(pm, x, y, dotv, dot_partial, xf, s);     /* best on class B (profiles/r01_run23) */
     } else if (pm.U >= 5) {
-        launch_panel_cfg<T, 5, 512>(pm, x, y, dotv, dot_partial, s);
+        launch_panel_cfg<T, 5, 512>(pm, x, y, dotv, dot_partial, xf, s);
     } else if (pm.U == 3) {
-        launch_panel_cfg<T, 3, 512>(pm, x, y, dotv, dot_partial, s);
+        launch_panel_cfg<T, 3, 512>(pm, x, y, dotv, dot_partial, xf, s);
     } else {
-        launch_panel_cfg<T, 4, 512>(pm, x, y, dotv, dot_partial, s);           /* <= 128 registers per thread */
+        launch_panel_cfg<T, 4, 512>(pm, x, y, dotv, dot_partial, xf, s);           /* <= 128 registers per thread */
     }
 }
-template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t, const double *, double *);
-template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t, const float *, float *);
+template void launch_panel<double>(const DevPanel &, const double *, double *, cudaStream_t, const double *, double *,
+                                   const XFlags *);
+template void launch_panel<float>(const DevPanel &, const float *, float *, cudaStream_t, const float *, float *,
+                                  const XFlags *);
 
 }  // namespace b200

@@ -7,7 +7,7 @@
 #   test [pytest -k expr]                     pytest -m gpu
 #   bench TAG [bench.py args]                 one-GPU bench line
 #   benchn N TAG [bench.py args]              N ranks under torch.distributed.run
-#   sweep TAG SHAPE "cfg,cfg,..." [iters]     scripts/sweep.py (kernel-only timing of layouts)
+#   sweep TAG SHAPE "cfg,cfg,..." [iters] [graph]   scripts/sweep.py (kernel-only timing of layouts; "graph": one CUDA graph replay)
 #   launches TAG [bench.py args]              ncu launch list (gpu__time_duration) of a short bench run
 #   ncufull TAG KERNEL_REGEX CMD...           one ncu --set full capture (+ raw/source CSV, stall summary)
 #   smoke                                     __graft_entry__.smoke()
@@ -29,8 +29,8 @@ benchn)
         --master-port $PORT bench.py --gpus $n "$@" > gpurun_out/$tag.json 2> gpurun_out/$tag.err
     echo "rc=$?"; cut -c1-400 gpurun_out/$tag.json; grep -v '^\*\|OMP_NUM\|^$\|^libb200' gpurun_out/$tag.err | tail -8 ;;
 sweep)
-    tag=$1; shape=$2; cfgs=$3; iters=${4:-50}
-    timeout 900 python scripts/sweep.py "$shape" "$cfgs" $iters 2>&1 | grep -v '^libb200' | tee -a gpurun_out/$tag.txt ;;
+    tag=$1; shape=$2; cfgs=$3; iters=${4:-50}; mode=${5:-}
+    timeout 900 python scripts/sweep.py "$shape" "$cfgs" $iters $mode 2>&1 | grep -v '^libb200' | tee -a gpurun_out/$tag.txt ;;
 launches)
     tag=$1; shift
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

@@ -1,5 +1,7 @@
 """Kernel-only timing sweep over panel geometry / kernel family on one NPB class.
-usage: python scripts/sweep.py C "16384x1024,8192x512,ordered,vector" [iters]"""
+usage: python scripts/sweep.py C "16384x1024,8192x512,ordered,vector" [iters] [graph]
+"graph": the launches are captured in one CUDA graph and the replay is timed -- for kernels of a
+few microseconds, which a Python loop of ctypes calls (~10 us per launch) cannot issue fast enough."""
 import os
 import sys
 import time
@@ -18,6 +20,7 @@ from lilac_benchmarks_b200 import libspmv, npb  # noqa: E402
 cls = sys.argv[1] if len(sys.argv) > 1 else "C"
 configs = (sys.argv[2] if len(sys.argv) > 2 else "16384x1024,ordered,vector").split(",")
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+use_graph = len(sys.argv) > 4 and sys.argv[4] == "graph"
 if cls.startswith("crsmat"):
     from lilac_benchmarks_b200 import gen
 
@@ -89,10 +92,21 @@ for cfg_full in configs:
         rm.exec(xs[i & 3], y)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        rm.exec(xs[i & 3], y)
-    e1.record()
+    if use_graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                rm.exec(xs[i & 3], y)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for i in range(iters):
+            rm.exec(xs[i & 3], y)
+        e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
     rm.exec(xs[0], y)

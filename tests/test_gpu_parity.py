@@ -859,3 +859,78 @@ def test_registered_vector_remapped_by_its_owner_is_caught(tmp_path):
     proc = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B200_SPMV_PIN_HOST="3"),
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0 and "remap ok" in proc.stdout, proc.stdout[-3000:]
+
+
+OVERLAP_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+import torch
+from lilac_benchmarks_b200 import libspmv, npb
+rng = np.random.default_rng(21)
+for cls, fmt in (("W", None), ("A", None), ("A", "2")):
+    if fmt:
+        os.environ["B200_SPMV_PANEL_FMT"] = fmt
+    m = npb.NpbMatrix(cls)
+    for x_pinned, y_pinned, off in ((False, False, 0), (True, True, 0), (True, False, 1), (False, True, 0)):
+        x = rng.standard_normal(m.n + 2 + off)
+        y = np.full(m.n, np.nan)
+        keep = []
+        if x_pinned:
+            keep.append(torch.from_numpy(x).pin_memory()); x = keep[-1].numpy()
+        if y_pinned:
+            keep.append(torch.from_numpy(y).pin_memory()); y = keep[-1].numpy()
+        xv = x[off:]
+        for rep in range(4):                       # the chunk flags carry the call number
+            xv[:] = rng.standard_normal(len(xv))
+            libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
+            assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx, omp=True)), (cls, fmt, x_pinned, y_pinned, off, rep)
+    # an in-place edit the guard cannot see (B200_SPMV_GUARD=0 here): the content checks run
+    # while the product is in flight, fail, and the call is redone on a fresh upload
+    up0 = libspmv.stats()["uploads"]
+    m.a[0] += 1.0
+    x = rng.standard_normal(m.n + 2); y = np.zeros(m.n)
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert libspmv.stats()["uploads"] == up0 + 1, (cls, fmt)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx, omp=True)), (cls, fmt, "redo")
+    libspmv.invalidate()
+    os.environ.pop("B200_SPMV_PANEL_FMT", None)
+# the sliced entry point on the paired layout, x NOT 16-byte aligned (cooperative slice loads)
+m = npb.NpbMatrix("W")
+rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+assert rm.kernel_name == "panel"
+xh = rng.standard_normal(m.n + 3)
+xd = torch.from_numpy(xh).cuda()
+yd = torch.zeros(m.n, dtype=torch.float64, device="cuda")
+flags = torch.full((4,), 7, dtype=torch.int64, device="cuda")      # all four slices of epoch 7 have landed
+cpr = (m.n + 3) // 4 // 2 * 2
+rc = rm.exec_sliced_ptr(xd.data_ptr() + 8, yd.data_ptr(), torch.cuda.current_stream().cuda_stream,
+                        flags.data_ptr(), 7, cpr, 4)
+assert rc >= 1, rc
+torch.cuda.synchronize()
+assert np.array_equal(yd.cpu().numpy(), oracle.spmv(m.a, xh[1:], m.rowstr, m.colidx))
+print("overlap ok")
+"""
+
+
+@pytest.mark.parametrize("chunks,flag_write", [(1, 1), (3, 1), (16, 1), (5, 0)])
+def test_x_uploaded_in_chunks_while_the_product_runs(tmp_path, chunks, flag_write):
+    """Drop-in path on one device: x goes up through the copy engine in `chunks` chunks on a
+    second stream while the PANEL / RING kernel runs and waits per chunk (b200_dropin.cu
+    run_call).  Forced on for small vectors here; pageable and pinned x / y, an x at an odd
+    offset, stream memory operations and plain 8-byte copies for the flags, the redo after a
+    failed content check, and the sliced entry point with a misaligned x."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "overlap.py"
+    script.write_text(OVERLAP_SCRIPT.format(root=root))
+    env = dict(os.environ, B200_SPMV_X_OVERLAP_MIN_KB="0", B200_SPMV_X_CHUNKS=str(chunks),
+               B200_SPMV_FLAG_WRITE=str(flag_write), B200_SPMV_GUARD="0")
+    proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert proc.returncode == 0 and "overlap ok" in proc.stdout, proc.stdout[-3000:]
