@@ -138,6 +138,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def stage(msg):
+    """Progress on stderr (the one JSON line owns stdout): says where a run that was cut off stood."""
+    if os.environ.get("B200_BENCH_QUIET"):
+        return
+    print(f"bench.py [{time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -307,9 +314,11 @@ def run_one_gpu(args):
     t0 = time.perf_counter()
     hm, npb_m = load_host_matrix(name)
     t_gen = time.perf_counter() - t0
+    stage(f"{hm.label}: host matrix ready ({t_gen:.1f} s)")
     t0 = time.perf_counter()
     rm = libspmv.ResidentMatrix(hm.a, hm.rowstr, hm.colidx, kernel=args.kernel)
     t_upload = time.perf_counter() - t0
+    stage(f"resident on the GPU ({rm.kernel_name}, {t_upload:.2f} s)")
     ncols = rm.ncols
     B = algorithmic_bytes(hm.nnz, hm.n, ncols)
     xs = [torch.from_numpy(rng.random(ncols + 2)).to(dev) for _ in range(4)]
@@ -338,17 +347,20 @@ def run_one_gpu(args):
     e2e_kernel_ms = st["kernel_ms"] / Ke
     e2e_devices = libspmv.devices_in_use()
     e2e_y = hy_np.copy()                       # result of the last call: x = hx_np[(Ke - 1) & 3]
+    stage(f"e2e, pinned caller vectors: {e2e_sec * 1e6:.1f} us per call")
     # pageable caller vectors (what NPB's COMMON arrays / pagerank's std::vectors are): pinned
     # bounce buffers inside the library, filled by its copy threads
     px = [np.array(v) for v in hx_np]
     py = np.zeros(hm.n)
     npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, 3)
     e2e_pageable_sec = npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, min(Ke, 500))
+    stage(f"e2e, pageable caller vectors: {e2e_pageable_sec * 1e6:.1f} us per call")
     # ... and the same pageable vectors with B200_SPMV_PIN_HOST=3 (opt-in): the library registers a
     # vector on its third sighting and checks the mapping on every call
     libspmv.lib().b200_spmv_set_auto_pin(3)
     npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, 16)
     e2e_autopin_sec = npb.time_spmv_calls(addr, py, hm.a, px, hm.rowstr, hm.colidx, hm.n, min(Ke, 500))
+    stage(f"e2e, pageable vectors registered on third sight: {e2e_autopin_sec * 1e6:.1f} us per call")
     libspmv.lib().b200_spmv_set_auto_pin(0)      # gives the registrations back ...
     libspmv.lib().b200_spmv_set_auto_pin(int(os.environ.get("B200_SPMV_PIN_HOST", "0") or 0))   # ... and restores the setting
     t0 = time.perf_counter()
@@ -358,9 +370,11 @@ def run_one_gpu(args):
 
     # ---- the headline: device-timed, after the end-to-end legs (clocks, TLB and L2 are in
     # the state a caller in the middle of a solve sees, not the state right after the upload)
+    stage("e2e legs done; device-timed steps")
     ms, clocks = time_steps(torch, step, K, W, barrier, 0)
     sec_per_step = ms / 1e3 / K
     value = B / sec_per_step / 1e9
+    stage(f"kernel: {sec_per_step * 1e6:.1f} us per step")
 
     peak, peak_src = measured_peak()
     line = {
@@ -393,11 +407,13 @@ def run_one_gpu(args):
 
     # ---- the callers of the ABI on this matrix ------------------------------
     if hm.kind == "npb" and not args.no_npb and name != "D":
+        stage("NPB CG through the ABI")
         res = npb.run_cg(npb_m, addr)
         line["npb_cg"] = {"class": name, "mops": res["mops"], "time_s": res["t_bench"],
                           "zeta": res["zeta"], "verified": res["verified"],
                           "spmv_calls": res["spmv_calls"], "vectors": "pageable host (as cg.f COMMON)"}
     if hm.kind == "npb" and not args.no_npb:
+        stage("NPB CG, device-resident")
         cls_ = hm.npb_class
         dres = rm.npb_cg_device(cls_.nonzer, cls_.niter, cls_.shift, use_graph=True)
         line["npb_cg_device_resident"] = {
@@ -421,6 +437,7 @@ def run_one_gpu(args):
 
     # ---- parity + CPU baseline beside it -------------------------------------
     if not args.no_cpu:
+        stage("CPU baseline and parity")
         x_host = xs[0].cpu().numpy()
         B_cpu = B
         est = B_cpu / 7.0e9

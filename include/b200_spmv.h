@@ -174,6 +174,9 @@ typedef struct {
     uint64_t d2h_bytes;        /* y traffic */
     uint64_t auto_pinned_calls;   /* calls that moved x or y through a vector this library registered */
     uint64_t auto_pin_revoked;    /* registrations dropped because the owner had remapped the memory */
+    uint64_t x_overlapped_calls;  /* calls whose x went up chunk by chunk (copy engine) while the product ran */
+    uint64_t x_overlap_timeouts;  /* ... whose product gave up waiting for a chunk (streams serialised by a
+                                   * profiler, CUDA_LAUNCH_BLOCKING, ...): redone the plain way, overlap off */
 } b200_spmv_stats;
 void b200_spmv_get_stats(b200_spmv_stats *out);
 void b200_spmv_reset_stats(void);

@@ -77,6 +77,7 @@ struct CacheEntry {
     int cols_per_part;         /* several devices: columns of x each device pulls (uniform) */
     unsigned long long epoch;  /* ... and the call number the flags carry */
     void *h_x, *h_y;           /* pinned bounce buffers (portable, mapped) */
+    void *h_x_alias, *h_y_alias;   /* ... as the devices address them */
     size_t x_bytes, y_bytes;
     int x_chunk_cols, x_nchunks;   /* one device: x goes up in this many chunks of this many columns */
     unsigned long long *h_epoch;   /* pinned: source of the flag copies when stream memory ops are unavailable */
@@ -93,8 +94,11 @@ static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 1;
 static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
 /* one device: x uploaded in chunks by the copy engine WHILE the product runs (the PANEL kernels
  * walk the columns left to right and wait per chunk) instead of in full before it */
-static int g_x_overlap = 1, g_x_chunks = 6;
+static int g_x_overlap = 1, g_x_chunks = 6, g_x_prelaunch = 0;
+static int g_x_overlap_auto = 0;   /* experiment: overlap also for vectors this library registered */
+static int g_x_test_stall = 0;     /* test hook: the last chunk's flag of the next overlapped call is never written */
 static size_t g_x_overlap_min = 256u << 10;
+static unsigned long long g_x_timeout_ns = 20ull * 1000 * 1000;    /* watchdog of the product's wait for a chunk */
 typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
 static StreamWriteValue32Fn g_write_value32 = nullptr;     /* cuStreamWriteValue32, through the runtime */
 
@@ -102,7 +106,7 @@ static StreamWriteValue32Fn g_write_value32 = nullptr;     /* cuStreamWriteValue
 struct AutoPin { char *lo, *hi; int seen; bool registered; bool failed; uint64_t last_use; };
 static std::vector<AutoPin> g_auto;
 /* what the probe kernels report about an auto-registered vector (pinned, mapped) */
-struct PinProbe { int x_bad; int pad; unsigned long long y_val[4]; };
+struct PinProbe { int x_bad; int x_timed_out; unsigned long long y_val[4]; };
 static PinProbe *g_probe = nullptr;
 struct RegSpan { char *lo, *hi; };              /* page-aligned host ranges registered by maybe_auto_pin */
 static std::vector<RegSpan> g_spans;
@@ -281,6 +285,10 @@ static void ensure_conf_locked(void)
         if (lb && atoi(lb) != 0) g_x_overlap = 0;
     }
     g_x_chunks = std::min(kMaxFlags, std::max(1, env_int("B200_SPMV_X_CHUNKS", 6)));
+    g_x_timeout_ns = (unsigned long long)std::max(1, env_int("B200_SPMV_X_TIMEOUT_MS", 20)) * 1000000ull;
+    g_x_prelaunch = env_int("B200_SPMV_X_PRELAUNCH", 0);
+    g_x_test_stall = env_int("B200_SPMV_X_TEST_STALL", 0);
+    g_x_overlap_auto = env_int("B200_SPMV_X_OVERLAP_AUTO", 0);      /* 1: every chunk is issued before the launch */
     g_x_overlap_min = (size_t)std::max(0, env_int("B200_SPMV_X_OVERLAP_MIN_KB", 256)) << 10;
     if (g_x_overlap && env_int("B200_SPMV_FLAG_WRITE", 1)) {
         void *fn = nullptr;
@@ -380,8 +388,16 @@ static uint64_t window_hash(const CacheEntry &e, size_t w)
  * pinned caller vectors
  * ---------------------------------------------------------------------- */
 /* Device-usable alias of a pinned (cudaHostAlloc'ed or registered) host range, or NULL
- * when any part of [p, p + bytes) is pageable: first and last byte must both be pinned
- * and map to device addresses `bytes - 1` apart (one mapping, or adjacent ones). */
+ * when any part of [p, p + bytes) is pageable.  First and last byte must both be pinned and
+ * map to device addresses `bytes - 1` apart; and since two registrations can sit at the two
+ * ends of a range whose middle is pageable (neighbouring vectors registered page by page), the
+ * allocations / registrations behind the addresses are walked (cuPointerGetAttribute
+ * RANGE_START_ADDR / RANGE_SIZE, obtained through the runtime) until they cover the range. */
+typedef int (*PointerGetAttributeFn)(void *, int, unsigned long long);
+static PointerGetAttributeFn g_ptr_attr = nullptr;
+static bool g_get_range_tried = false;
+static const int kAttrRangeStart = 11, kAttrRangeSize = 12;   /* CU_POINTER_ATTRIBUTE_RANGE_START_ADDR / _SIZE */
+
 static void *pinned_device_alias(const void *p, size_t bytes)
 {
     if (bytes == 0) return nullptr;
@@ -391,6 +407,29 @@ static void *pinned_device_alias(const void *p, size_t bytes)
     if (cudaPointerGetAttributes(&a1, (const char *)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (a1.type != cudaMemoryTypeHost || !a1.devicePointer) return nullptr;
     if ((char *)a1.devicePointer - (char *)a0.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;
+    if (!g_get_range_tried) {
+        g_get_range_tried = true;
+        void *fn = nullptr;
+        enum cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_ptr_attr = (PointerGetAttributeFn)fn;
+        else
+            cudaGetLastError();
+    }
+    if (g_ptr_attr) {
+        const unsigned long long lo = (unsigned long long)(uintptr_t)p, hi = lo + bytes;
+        unsigned long long at = lo;
+        for (int hops = 0; at < hi; ++hops) {
+            unsigned long long base = 0;
+            size_t size = 0;
+            const bool ok = g_ptr_attr(&base, kAttrRangeStart, at) == 0 && g_ptr_attr(&size, kAttrRangeSize, at) == 0 &&
+                            size > 0 && base <= at;
+            if (!ok && hops == 0) { g_ptr_attr = nullptr; break; }   /* no ranges for host memory here: ends only */
+            if (!ok || hops > 64) return nullptr;                    /* a pageable hole in the middle */
+            at = base + size;                                        /* the next range must start right here */
+        }
+    }
     return a0.devicePointer;
 }
 
@@ -592,6 +631,8 @@ static void build_entry_locked(CacheEntry &e)
     }
     CUDA_OK(cudaHostAlloc(&e.h_x, e.x_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     CUDA_OK(cudaHostAlloc(&e.h_y, e.y_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    CUDA_OK(cudaHostGetDevicePointer(&e.h_x_alias, e.h_x, 0));
+    CUDA_OK(cudaHostGetDevicePointer(&e.h_y_alias, e.h_y, 0));
     CUDA_OK(cudaHostAlloc((void **)&e.h_epoch, kMaxFlags * sizeof(unsigned long long), cudaHostAllocPortable));
     memset(e.h_epoch, 0, kMaxFlags * sizeof(unsigned long long));
     /* chunks of the overlapped upload: a multiple of 2048 columns each (whole 16-byte granules
@@ -701,6 +742,7 @@ static CacheEntry *lookup_locked(const void *a, const int *rowstr, const int *co
  * ---------------------------------------------------------------------- */
 enum CallResult {
     CALL_OK = 0,
+    CALL_REDO_PLAIN,       /* the product gave up waiting for a chunk of x (overlap is off from now on): redo */
     CALL_REDO_BOUNCE,      /* an auto-registered vector turned out to be remapped (revoked): redo without it */
     CALL_STALE_MATRIX      /* the content checks failed: the resident copy is out of date, re-upload and redo */
 };
@@ -752,8 +794,14 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
      * behind flags -- was built and measured: a GPU-issued PCIe read takes ~10 us to come
      * back, a window of chunks in flight serialises on that, and without a window the chunks
      * do not land in column order: 208 us per call against 157 us, profiles/r02_run13_bench_C*.json.) */
-    const bool overlap = !multi && g_x_overlap && x_used >= g_x_overlap_min && x_used > 0 &&
-                         e.part[0].m && exec_takes_flags(e.part[0].m) && e.x_nchunks <= kMaxFlags;
+    /* Not for a vector this library registered itself (B200_SPMV_PIN_HOST): the copy engine
+     * reading such memory while the product spins did not make progress on the test box
+     * (bench.py's auto-pin leg hung; profiles/r02_run29_bench_C.err) -- those calls keep the
+     * copy kernel.  And the wait has a watchdog: whatever else may serialise the two streams
+     * costs one timeout, after which the overlap is off for the process. */
+    const bool overlap = !multi && g_x_overlap && x_used >= g_x_overlap_min && x_used > 0 && (!x_auto || g_x_overlap_auto) &&
+                         e.part[0].m && exec_takes_guarded_flags(e.part[0].m) && e.x_nchunks <= kMaxFlags;
+    if (overlap) g_probe->x_timed_out = 0;
 
     /* x: host -> device (gpu.c:264).  Without the overlap, pinned caller memory is read in
      * place over PCIe by a copy kernel on the library's stream; pageable memory goes through
@@ -768,8 +816,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             x_bounce = true;
             if (!overlap) memcpy(e.h_x, iv, x_used);
             x_pinned = (const char *)e.h_x;
-            x_alias = (const char *)pinned_device_alias(e.h_x, x_used);
-            if (!x_alias) die("the pinned bounce buffer has no device alias");
+            x_alias = (const char *)e.h_x_alias;
         }
     }
     /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
@@ -777,7 +824,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
     char *y_alias = y_avoid ? nullptr : (char *)pinned_device_alias(ov, (size_t)n * es);
     const bool y_direct = y_alias != nullptr;
     char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
-    if (!y_direct) y_alias = (char *)pinned_device_alias(e.h_y, (size_t)n * es);
+    if (!y_direct) y_alias = (char *)e.h_y_alias;
 
     /* one cudaSetDevice per device and loop, restored once at the end: with eight devices
      * the host side of a call is a few dozen runtime calls, and it is the critical path
@@ -803,6 +850,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             if (x_bounce) memcpy((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
             CUDA_OK(cudaMemcpyAsync(pt.d_x + lo, x_pinned + lo, hi - lo, cudaMemcpyHostToDevice, pt.ctx->copy_stream));
         }
+        if (g_x_test_stall && k == e.x_nchunks - 1) { g_x_test_stall = 0; return; }    /* the watchdog's test */
         write_flag(pt.ctx->copy_stream, pt.d_flags + k, epoch, e.h_epoch + k);
     };
     for (int p = 0; p < e.nparts; ++p) {
@@ -825,7 +873,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             launch_copy_in_multi_flagged(x_alias ? x_alias + pt.x_lo : nullptr, dst, e.nparts, bytes, flag,
                                          epoch, pt.d_counter, s);
         } else if (overlap) {
-            send_chunk(0);
+            for (int k = 0; k < (g_x_prelaunch ? e.x_nchunks : 1); ++k) send_chunk(k);
         } else if (bytes > 0) {
             if (g_zero_copy) {
                 void *dst[1] = {pt.d_x + pt.x_lo};
@@ -851,11 +899,11 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
             y_target = y_alias + (size_t)pt.row_lo * es;
         if (overlap) {
-            SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks};
+            SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks, &g_probe->x_timed_out, g_x_timeout_ns};
             launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
         } else if (multi && exec_waits_in_kernel(pt.m)) {
             /* the ring kernel waits per slice, just before the panels that need it */
-            SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts};
+            SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts, nullptr, 0ull};
             launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
         } else {
             if (multi) launch_wait_flags(pt.d_flags, e.nparts, epoch, s);
@@ -870,7 +918,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             y_probed = true;
         }
     }
-    if (overlap)                                   /* the rest of x follows the launch */
+    if (overlap && !g_x_prelaunch)                 /* the rest of x follows the launch */
         for (int k = 1; k < e.x_nchunks; ++k) send_chunk(k);
     /* the GPU is busy: now the content checks of the cache hit */
     const bool matrix_stale = check_content && entry_content_stale(e);
@@ -881,6 +929,17 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
     if (timed_part >= 0)
         CUDA_OK(cudaEventElapsedTime(&kernel_ms, e.part[timed_part].ctx->ev0, e.part[timed_part].ctx->ev1));
     use(saved_dev);
+    if (overlap) {
+        g_stats.x_overlapped_calls++;
+        if (g_probe->x_timed_out) {
+            g_stats.x_overlap_timeouts++;
+            g_x_overlap = 0;
+            fprintf(stderr, "libb200-spmv: the product waited %llu ms for a chunk of x that the copy stream "
+                            "did not deliver (streams serialised?); uploading x before the product from now on\n",
+                    g_x_timeout_ns / 1000000ull);
+            return CALL_REDO_PLAIN;
+        }
+    }
     if (matrix_stale) return CALL_STALE_MATRIX;
     /* an auto-registered range whose owner has remapped it: the GPU read / wrote the OLD
      * pages.  Revoke the registration and have the call redone through the bounce buffer. */

@@ -753,6 +753,13 @@ bool exec_takes_flags(const b200_matrix *m)
     return m->kernel == B200_KERNEL_PANEL && (m->panel.fmt == 2 || m->panel.fmt == 0);
 }
 
+/* ... with a watchdog on the wait (the drop-in path's overlapped upload): the paired kernel's
+ * flagged instance only; the ring kernel's spin is left exactly as the multi-GPU runs measured it */
+bool exec_takes_guarded_flags(const b200_matrix *m)
+{
+    return m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 0;
+}
+
 int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
                 const XPush *xp)
 {
@@ -760,8 +767,9 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
     int launched_kernels = 1;
     if (m->kernel == B200_KERNEL_PANEL) {
         if (m->panel.fmt == 2) {
-            XFlags xf = {nullptr, 0ull, 1, 0};
-            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks; }
+            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull};
+            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks;
+                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; }
             XPush none;
             none.src = nullptr;
             const XPush &push = xp ? *xp : none;
@@ -770,8 +778,9 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
             else
                 launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, push, s);
         } else {
-            XFlags xf = {nullptr, 0ull, 1, 0};
-            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks; }
+            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull};
+            if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks;
+                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; }
             if (m->dtype == B200_F64)
                 launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s, nullptr, nullptr,
                                      xf.flags ? &xf : nullptr);
@@ -866,7 +875,7 @@ extern "C" int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y,
     if (!m) die("b200_spmv_exec_sliced: null matrix");
     if (!exec_takes_flags(m)) return -1;
     DeviceScope scope(m->device);
-    SliceFlags sf = {flags, epoch, cols_per_rank, nranks};
+    SliceFlags sf = {flags, epoch, cols_per_rank, nranks, nullptr, 0ull};
     return exec_locked(m, d_x, d_y, (cudaStream_t)stream, &sf);
 }
 
@@ -891,7 +900,7 @@ extern "C" int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, vo
                                 &vflags, &cpr) != 0)
         return -1;
     DeviceScope scope(m->device);
-    SliceFlags sf = {vflags, epoch, cols_per_rank, xp.nranks};
+    SliceFlags sf = {vflags, epoch, cols_per_rank, xp.nranks, nullptr, 0ull};
     return exec_locked(m, xbuf, d_y, (cudaStream_t)stream, &sf, &xp);
 }
 

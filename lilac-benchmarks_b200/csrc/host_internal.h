@@ -98,6 +98,8 @@ struct SliceFlags {
     unsigned long long epoch;
     int cols_per_rank;
     int nranks;
+    int *timed_out;                     /* watchdog, see XFlags; NULL: none */
+    unsigned long long timeout_ns;
 };
 
 b200_matrix *upload_locked(DevCtx *ctx, const void *a, const int *rowstr, const int *colidx,
@@ -109,6 +111,7 @@ void release_locked(b200_matrix *m);
 int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, const SliceFlags *sf,
                 const XPush *xp = nullptr);
 bool exec_takes_flags(const b200_matrix *m);        /* paired PANEL and RING kernels */
+bool exec_takes_guarded_flags(const b200_matrix *m);    /* paired PANEL kernel: flags with a watchdog on the wait */
 bool exec_waits_in_kernel(const b200_matrix *m);    /* RING kernel: flags and the fused push (multi-GPU paths) */
 
 }  // namespace b200

@@ -71,13 +71,38 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsign
 /* x that arrives slice by slice (XFlags: from other GPUs over NVLink, or from the host through
  * the copy engine while the product runs): before a panel's x slice is requested, the slices
  * holding its columns [cbase, cbase + cw) must have landed.  Columns are walked left to right,
- * so `ready` (slices [0, ready) have arrived) only grows.  One thread calls this. */
+ * so `ready` (slices [0, ready) have arrived) only grows.  One thread calls this.
+ * The spin is out of line (it is off the common path and the paired kernel has no register to
+ * spare) and, when the launcher asks for it, guarded by a watchdog: a product that waits for
+ * copies issued on ANOTHER stream never ends if something serialises the streams (a profiler
+ * replaying kernels, CUDA_LAUNCH_BLOCKING, one hardware queue) -- after timeout_ns it reports
+ * *timed_out = 1 and goes on with whatever x holds; the host redoes the call the plain way. */
+static __device__ __noinline__ int wait_x_slices_spin(const unsigned long long *flags, unsigned long long epoch,
+                                                      int ready, int r1, int *timed_out,
+                                                      unsigned long long timeout_ns)
+{
+    unsigned long long t0 = 0;
+    for (; ready <= r1; ++ready) {
+        while (ld_acquire_sys_u64(flags + ready) < epoch) {
+            if (timed_out) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > timeout_ns) {
+                    *reinterpret_cast<volatile int *>(timed_out) = 1;
+                    return 1 << 30;                  /* this CTA waits for nothing any more */
+                }
+            }
+        }
+    }
+    return ready;
+}
+
 __device__ __forceinline__ void wait_x_slices(const XFlags &xf, int &ready, int cbase, int cw)
 {
     const int r1 = min((cbase + cw - 1) / xf.cols_per_rank, xf.nranks - 1);
     if (r1 < ready) return;
-    for (; ready <= r1; ++ready)
-        while (ld_acquire_sys_u64(xf.flags + ready) < xf.epoch) { }
+    ready = wait_x_slices_spin(xf.flags, xf.epoch, ready, r1, xf.timed_out, xf.timeout_ns);
     /* the slice was written through the generic proxy (another GPU) or by a copy engine, the
      * bulk copy reads it through the async proxy */
     asm volatile("fence.proxy.async.global;" ::: "memory");

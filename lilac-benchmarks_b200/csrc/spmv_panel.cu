@@ -451,7 +451,7 @@ void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T 
                   const XFlags *flags)
 {
     if (pm.nblk <= 0) return;
-    const XFlags none = {nullptr, 0ull, 1, 0};
+    const XFlags none = {nullptr, 0ull, 1, 0, nullptr, 0ull};
     const XFlags &xf = flags ? *flags : none;
     const int threads = pm.R / pm.G;
     if (threads <= 256 && pm.U >= 5) {

@@ -36,7 +36,8 @@ class Stats(C.Structure):
     _fields_ = [("calls", c_uint64), ("uploads", c_uint64), ("kernel_launches", c_uint64),
                 ("kernel_ms", c_double), ("e2e_ms", c_double), ("upload_ms", c_double),
                 ("h2d_bytes", c_uint64), ("d2h_bytes", c_uint64),
-                ("auto_pinned_calls", c_uint64), ("auto_pin_revoked", c_uint64)]
+                ("auto_pinned_calls", c_uint64), ("auto_pin_revoked", c_uint64),
+                ("x_overlapped_calls", c_uint64), ("x_overlap_timeouts", c_uint64)]
 
 
 _lib = None

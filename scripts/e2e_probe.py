@@ -1,5 +1,6 @@
 """Time the drop-in ABI call (host vectors) on one NPB class; library knobs come from the env.
-usage: [B200_SPMV_ZEROCOPY=0|1] [B200_SPMV_PIN_HOST=1] python scripts/e2e_probe.py C pinned|pageable [iters]"""
+usage: [B200_SPMV_ZEROCOPY=0|1] [B200_SPMV_PIN_HOST=1] python scripts/e2e_probe.py C pinned|pageable|registered [iters]
+(registered: pageable numpy vectors handed to b200_spmv_pin_host, i.e. cudaHostRegister)"""
 import sys
 import time
 from pathlib import Path
@@ -22,11 +23,26 @@ rng = np.random.default_rng(0)
 if mode == "pinned":
     hx = [torch.from_numpy(rng.random(m.n + 2)).pin_memory().numpy() for _ in range(4)]
     hy = torch.zeros(m.n, dtype=torch.float64).pin_memory().numpy()
+elif mode == "registered":
+    # one pageable buffer, registered whole (cudaHostRegister), the five vectors carved out of it
+    per = (m.n + 2 + 511) // 512 * 512
+    buf = np.zeros(5 * per + 1024)
+    lo = (buf.ctypes.data + 4095) // 4096 * 4096
+    first = (lo - buf.ctypes.data) // 8
+    nbytes = (5 * per * 8) // 4096 * 4096
+    rc = libspmv.lib().b200_spmv_pin_host(lo, nbytes)
+    print(f"registered {nbytes} bytes: rc={rc}", file=sys.stderr, flush=True)
+    hx = [buf[first + k * per:first + k * per + m.n + 2] for k in range(4)]
+    for v in hx:
+        v[:] = rng.random(m.n + 2)
+    hy = buf[first + 4 * per:first + 4 * per + m.n]
 else:
     hx = [rng.random(m.n + 2) for _ in range(4)]
     hy = np.zeros(m.n)
+print(f"{cls} {mode}: matrix ready", file=sys.stderr, flush=True)
 for i in range(8):
     libspmv.spmv_harness(hy, m.a, hx[i & 3], m.rowstr, m.colidx, m.n)
+    print(f"{cls} {mode}: call {i} done", file=sys.stderr, flush=True)
 libspmv.reset_stats()
 t0 = time.perf_counter()
 for i in range(iters):
@@ -36,4 +52,5 @@ st = libspmv.stats()
 import os
 knobs = {k: v for k, v in os.environ.items() if k.startswith("B200_SPMV")}
 print(f"{cls} {mode:9s} {knobs}  e2e {dt * 1e6:8.1f} us/call  kernel {st['kernel_ms'] / iters * 1e3:7.1f} us  "
-      f"lib-internal {st['e2e_ms'] / iters * 1e3:7.1f} us", flush=True)
+      f"lib-internal {st['e2e_ms'] / iters * 1e3:7.1f} us  overlapped {st['x_overlapped_calls']} "
+      f"timeouts {st['x_overlap_timeouts']}", flush=True)

@@ -934,3 +934,41 @@ def test_x_uploaded_in_chunks_while_the_product_runs(tmp_path, chunks, flag_writ
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0 and "overlap ok" in proc.stdout, proc.stdout[-3000:]
+
+
+WATCHDOG_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as entry
+entry.load_package()
+oracle = entry.load_oracle()
+from lilac_benchmarks_b200 import libspmv, npb
+m = npb.NpbMatrix("A")
+rng = np.random.default_rng(33)
+x = rng.standard_normal(m.n + 2); y = np.zeros(m.n)
+for call in range(3):
+    x[:] = rng.standard_normal(m.n + 2)
+    libspmv.spmv_harness(y, m.a, x, m.rowstr, m.colidx, m.n)
+    assert np.array_equal(y, oracle.spmv(m.a, x, m.rowstr, m.colidx)), call
+st = libspmv.stats()
+assert st["x_overlapped_calls"] == 1 and st["x_overlap_timeouts"] == 1, st
+print("watchdog ok")
+"""
+
+
+def test_product_that_never_gets_its_chunk_times_out_and_is_redone(tmp_path):
+    """The overlapped upload's watchdog: a chunk flag that never arrives (test hook; in the
+    field: streams serialised by a profiler) ends the in-kernel wait after the timeout, the call
+    is redone with x uploaded before the product, and the overlap stays off."""
+    import os
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "watchdog.py"
+    script.write_text(WATCHDOG_SCRIPT.format(root=root))
+    env = dict(os.environ, B200_SPMV_X_OVERLAP_MIN_KB="0", B200_SPMV_X_CHUNKS="4", B200_SPMV_X_TEST_STALL="1",
+               B200_SPMV_X_TIMEOUT_MS="5")
+    proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "watchdog ok" in proc.stdout, proc.stdout[-3000:]
