@@ -344,7 +344,15 @@ def run_one_gpu(args):
     e2e_sec = npb.time_spmv_calls(addr, hy_np, hm.a, hx_np, hm.rowstr, hm.colidx, hm.n, Ke)
     st = libspmv.stats()
     h2d, d2h = st["h2d_bytes"] // Ke, st["d2h_bytes"] // Ke
-    e2e_kernel_ms = st["kernel_ms"] / Ke
+    e2e_overlapped = st["x_overlapped_calls"]
+    # where the time of such a call goes: the same calls once more with the library's CUDA-event
+    # timing of the product switched on (off by default: it costs ~3 us per call)
+    libspmv.lib().b200_spmv_set_time_kernels(1)
+    libspmv.reset_stats()
+    Kt = min(Ke, 100)
+    npb.time_spmv_calls(addr, hy_np, hm.a, hx_np, hm.rowstr, hm.colidx, hm.n, Kt)
+    e2e_kernel_ms = libspmv.stats()["kernel_ms"] / Kt
+    libspmv.lib().b200_spmv_set_time_kernels(0)
     e2e_devices = libspmv.devices_in_use()
     e2e_y = hy_np.copy()                       # result of the last call: x = hx_np[(Ke - 1) & 3]
     stage(f"e2e, pinned caller vectors: {e2e_sec * 1e6:.1f} us per call")
@@ -398,6 +406,12 @@ def run_one_gpu(args):
                        + (f", one process driving {e2e_devices} GPUs (B200_SPMV_DEVICES)" if e2e_devices > 1 else ""),
                 "devices": e2e_devices,
                 "kernel_ms_per_step": e2e_kernel_ms,
+                "kernel_ms_note": "CUDA events around the product inside the call (separate leg with the library's "
+                                  "event timing on): includes its wait for the first chunk of x and the y stores "
+                                  "over PCIe",
+                "x_upload": (f"overlapped with the product: {e2e_overlapped} of {Ke} calls (first chunk by a "
+                             "PCIe-reading copy kernel, the rest by the copy engine behind per-chunk flags)")
+                if e2e_overlapped else "copy kernel before the product",
                 "pageable_ms_per_step": e2e_pageable_sec * 1e3,
                 "pageable_value": B / e2e_pageable_sec / 1e9,
                 "pageable_pin_host_3_ms_per_step": e2e_autopin_sec * 1e3,
@@ -650,6 +664,11 @@ def run_multi_gpu(args, world, rank, local_rank):
             Ke = max(10, min(K, 200))
             e2e_sec = npb.time_spmv_calls(addr, hy_np, a_h, hx_np, rs_h, ci_h, cls.na, Ke)
             st = libspmv.stats()
+            libspmv.lib().b200_spmv_set_time_kernels(1)
+            libspmv.reset_stats()
+            npb.time_spmv_calls(addr, hy_np, a_h, hx_np, rs_h, ci_h, cls.na, min(Ke, 50))
+            st["kernel_ms"] = libspmv.stats()["kernel_ms"] * Ke / min(Ke, 50)
+            libspmv.lib().b200_spmv_set_time_kernels(0)
             px = [np.array(v) for v in hx_np]
             py = np.zeros(cls.na)
             npb.time_spmv_calls(addr, py, a_h, px, rs_h, ci_h, cls.na, 2)

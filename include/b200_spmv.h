@@ -180,6 +180,10 @@ typedef struct {
 } b200_spmv_stats;
 void b200_spmv_get_stats(b200_spmv_stats *out);
 void b200_spmv_reset_stats(void);
+/* CUDA-event timing of the product inside every drop-in call (feeds kernel_ms above).  Off by
+ * default -- two event records and a query per call are ~3 us of a 130 us call --;
+ * B200_SPMV_TIME_KERNELS=1 or this switch turn it on. */
+void b200_spmv_set_time_kernels(int on);
 
 /* Pin a caller-owned host vector so x / y move in place over PCIe instead of through the
  * library's pinned bounce buffer (class C: 0.15 ms per call instead of 0.29 ms).  Either the

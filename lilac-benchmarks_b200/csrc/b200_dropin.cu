@@ -90,11 +90,12 @@ static std::vector<PinnedRange> g_pinned;
 static uint64_t g_tick = 0;
 static b200_spmv_stats g_stats;
 static bool g_conf_ready = false;
-static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 1;
+static int g_validate = 1, g_cache_cap = 4, g_time_kernels = 0;
 static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
 /* one device: x uploaded in chunks by the copy engine WHILE the product runs (the PANEL kernels
  * walk the columns left to right and wait per chunk) instead of in full before it */
 static int g_x_overlap = 1, g_x_chunks = 6, g_x_prelaunch = 0;
+static int g_x_first_kernel = 1;   /* the first chunk by the PCIe-reading copy kernel on the product's stream */
 static int g_x_overlap_auto = 0;   /* experiment: overlap also for vectors this library registered */
 static int g_x_test_stall = 0;     /* test hook: the last chunk's flag of the next overlapped call is never written */
 static size_t g_x_overlap_min = 256u << 10;
@@ -110,6 +111,7 @@ struct PinProbe { int x_bad; int x_timed_out; unsigned long long y_val[4]; };
 static PinProbe *g_probe = nullptr;
 struct RegSpan { char *lo, *hi; };              /* page-aligned host ranges registered by maybe_auto_pin */
 static std::vector<RegSpan> g_spans;
+static uint64_t g_reg_events = 0;               /* cudaHostRegister / Unregister calls made by this library */
 static int g_ndev = 0, g_devs[kMaxDevices];
 static int64_t g_multi_min_nnz = 1 << 22;
 
@@ -272,7 +274,7 @@ static void ensure_conf_locked(void)
     if (g_conf_ready) return;
     g_validate = env_int("B200_SPMV_VALIDATE", 1);
     g_cache_cap = std::max(1, env_int("B200_SPMV_CACHE", 4));
-    g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 1);
+    g_time_kernels = env_int("B200_SPMV_TIME_KERNELS", 0);
     g_zero_copy = env_int("B200_SPMV_ZEROCOPY", 1);
     g_auto_pin = std::max(0, env_int("B200_SPMV_PIN_HOST", 0));
     CUDA_OK(cudaHostAlloc((void **)&g_probe, sizeof(PinProbe), cudaHostAllocPortable | cudaHostAllocMapped));
@@ -288,7 +290,8 @@ static void ensure_conf_locked(void)
     g_x_timeout_ns = (unsigned long long)std::max(1, env_int("B200_SPMV_X_TIMEOUT_MS", 20)) * 1000000ull;
     g_x_prelaunch = env_int("B200_SPMV_X_PRELAUNCH", 0);
     g_x_test_stall = env_int("B200_SPMV_X_TEST_STALL", 0);
-    g_x_overlap_auto = env_int("B200_SPMV_X_OVERLAP_AUTO", 0);      /* 1: every chunk is issued before the launch */
+    g_x_overlap_auto = env_int("B200_SPMV_X_OVERLAP_AUTO", 0);
+    g_x_first_kernel = env_int("B200_SPMV_X_FIRST_KERNEL", 1);      /* 1: every chunk is issued before the launch */
     g_x_overlap_min = (size_t)std::max(0, env_int("B200_SPMV_X_OVERLAP_MIN_KB", 256)) << 10;
     if (g_x_overlap && env_int("B200_SPMV_FLAG_WRITE", 1)) {
         void *fn = nullptr;
@@ -435,6 +438,7 @@ static void *pinned_device_alias(const void *p, size_t bytes)
 
 static int register_range_locked(void *p, size_t bytes)
 {
+    ++g_reg_events;
     cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) { cudaGetLastError(); return -1; }
     PinnedRange r = {(char *)p, (char *)p + bytes};
@@ -509,6 +513,7 @@ static bool maybe_auto_pin(const void *p, size_t bytes)
     char *shi = (char *)(((uintptr_t)hi + page - 1) / page * page);
     for (size_t i = 0; i < g_spans.size();) {
         if (g_spans[i].lo <= shi && slo <= g_spans[i].hi) {            /* overlaps or abuts */
+            ++g_reg_events;
             cudaHostUnregister(g_spans[i].lo);
             cudaGetLastError();
             slo = std::min(slo, g_spans[i].lo);
@@ -520,6 +525,7 @@ static bool maybe_auto_pin(const void *p, size_t bytes)
             ++i;
         }
     }
+    ++g_reg_events;
     if (cudaHostRegister(slo, (size_t)(shi - slo), cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         cudaGetLastError();
         /* e.g. the span touches memory registered by somebody else: nothing of it is ours now */
@@ -541,6 +547,7 @@ static void auto_pin_revoke(const void *p)
     const char *c = (const char *)p;
     for (size_t i = 0; i < g_spans.size(); ++i) {
         if (c < g_spans[i].lo || c >= g_spans[i].hi) continue;
+        ++g_reg_events;
         cudaHostUnregister(g_spans[i].lo);
         cudaGetLastError();
         for (AutoPin &a : g_auto)
@@ -768,6 +775,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
 {
     const size_t es = elem_size(dtype);
     const size_t x_used = (size_t)e.ncols * es;
+    static uint64_t reg_events_seen = 0;
     /* memory registered by this library is only ever used with the probes on; a range that
      * merely touches such memory (or a redo after a failed probe) takes the bounce buffer */
     const bool x_auto = allow_auto && x_used > 0 && maybe_auto_pin(iv, x_used);
@@ -794,12 +802,19 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
      * behind flags -- was built and measured: a GPU-issued PCIe read takes ~10 us to come
      * back, a window of chunks in flight serialises on that, and without a window the chunks
      * do not land in column order: 208 us per call against 157 us, profiles/r02_run13_bench_C*.json.) */
-    /* Not for a vector this library registered itself (B200_SPMV_PIN_HOST): the copy engine
-     * reading such memory while the product spins did not make progress on the test box
-     * (bench.py's auto-pin leg hung; profiles/r02_run29_bench_C.err) -- those calls keep the
-     * copy kernel.  And the wait has a watchdog: whatever else may serialise the two streams
-     * costs one timeout, after which the overlap is off for the process. */
-    const bool overlap = !multi && g_x_overlap && x_used >= g_x_overlap_min && x_used > 0 && (!x_auto || g_x_overlap_auto) &&
+    /* Not in a call that has just (un)registered host memory: the driver applies the change
+     * to the GPU's address space with the next work it submits, and that did not get past a
+     * product spinning on all SMs -- copies queued behind it never ran (bench.py's auto-pin
+     * leg hung in the calls that registered a vector; profiles/r02_run29_bench_C.err,
+     * r02_run31_e2e_variants.txt).  Such a call uploads x before the product, and its stream
+     * synchronisation flushes the change.  Vectors this library registered itself stay with
+     * the copy kernel altogether unless B200_SPMV_X_OVERLAP_AUTO=1.  Whatever ELSE may
+     * serialise the two streams (a registration by another thread, a profiler) costs one
+     * watchdog timeout, after which the overlap is off for the process. */
+    const bool reg_changed = g_reg_events != reg_events_seen;
+    reg_events_seen = g_reg_events;
+    const bool overlap = !multi && g_x_overlap && x_used >= g_x_overlap_min && x_used > 0 && !reg_changed &&
+                         (!x_auto || g_x_overlap_auto) &&
                          e.part[0].m && exec_takes_guarded_flags(e.part[0].m) && e.x_nchunks <= kMaxFlags;
     if (overlap) g_probe->x_timed_out = 0;
 
@@ -842,14 +857,23 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
     }
     const unsigned long long epoch = ++e.epoch;
     /* chunk k of the overlapped upload: (memcpy into the bounce buffer,) copy, flag */
+    /* The first chunk is on the critical path (the product cannot start without it): a copy
+     * engine transfer takes ~20 us from the call to the flag, the PCIe-reading copy kernel
+     * on the product's own stream -- no flag needed, stream order -- about half of that. */
+    const bool first_by_kernel = overlap && g_x_first_kernel && g_zero_copy;
+    int x_sent = 0;                                /* chunks requested so far */
     auto send_chunk = [&](int k) {
         Part &pt = e.part[0];
         const size_t lo = std::min(x_used, (size_t)k * e.x_chunk_cols * es);
         const size_t hi = std::min(x_used, (size_t)(k + 1) * e.x_chunk_cols * es);
-        if (hi > lo) {
-            if (x_bounce) memcpy((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
-            CUDA_OK(cudaMemcpyAsync(pt.d_x + lo, x_pinned + lo, hi - lo, cudaMemcpyHostToDevice, pt.ctx->copy_stream));
+        if (hi > lo && x_bounce) memcpy((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
+        if (k == 0 && first_by_kernel) {
+            void *dst[1] = {pt.d_x};
+            if (hi > lo) launch_copy_in_multi(x_alias, dst, 1, hi - lo, pt.ctx->stream);
+            return;
         }
+        if (hi > lo)
+            CUDA_OK(cudaMemcpyAsync(pt.d_x + lo, x_pinned + lo, hi - lo, cudaMemcpyHostToDevice, pt.ctx->copy_stream));
         if (g_x_test_stall && k == e.x_nchunks - 1) { g_x_test_stall = 0; return; }    /* the watchdog's test */
         write_flag(pt.ctx->copy_stream, pt.d_flags + k, epoch, e.h_epoch + k);
     };
@@ -873,7 +897,10 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             launch_copy_in_multi_flagged(x_alias ? x_alias + pt.x_lo : nullptr, dst, e.nparts, bytes, flag,
                                          epoch, pt.d_counter, s);
         } else if (overlap) {
-            for (int k = 0; k < (g_x_prelaunch ? e.x_nchunks : 1); ++k) send_chunk(k);
+            /* with the first chunk on the product's stream, the second one (copy engine: ~20 us
+             * from here to its flag) is requested before the launch as well */
+            x_sent = g_x_prelaunch ? e.x_nchunks : std::min(e.x_nchunks, first_by_kernel ? 2 : 1);
+            for (int k = 0; k < x_sent; ++k) send_chunk(k);
         } else if (bytes > 0) {
             if (g_zero_copy) {
                 void *dst[1] = {pt.d_x + pt.x_lo};
@@ -899,11 +926,12 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
             y_target = y_alias + (size_t)pt.row_lo * es;
         if (overlap) {
-            SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks, &g_probe->x_timed_out, g_x_timeout_ns};
+            SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks, &g_probe->x_timed_out, g_x_timeout_ns,
+                             first_by_kernel ? 1 : 0};
             launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
         } else if (multi && exec_waits_in_kernel(pt.m)) {
             /* the ring kernel waits per slice, just before the panels that need it */
-            SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts, nullptr, 0ull};
+            SliceFlags sf = {pt.d_flags, epoch, e.cols_per_part, e.nparts, nullptr, 0ull, 0};
             launched += exec_locked(pt.m, pt.d_x, y_target ? y_target : pt.d_y, s, &sf);
         } else {
             if (multi) launch_wait_flags(pt.d_flags, e.nparts, epoch, s);
@@ -918,8 +946,8 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             y_probed = true;
         }
     }
-    if (overlap && !g_x_prelaunch)                 /* the rest of x follows the launch */
-        for (int k = 1; k < e.x_nchunks; ++k) send_chunk(k);
+    if (overlap)                                   /* the rest of x follows the launch */
+        for (int k = x_sent; k < e.x_nchunks; ++k) send_chunk(k);
     /* the GPU is busy: now the content checks of the cache hit */
     const bool matrix_stale = check_content && entry_content_stale(e);
     float kernel_ms = 0.f;
@@ -1037,13 +1065,21 @@ extern "C" void b200_spmv_reset_stats(void)
     pthread_mutex_unlock(&g_lock);
 }
 
+extern "C" void b200_spmv_set_time_kernels(int on)
+{
+    pthread_mutex_lock(&g_lock);
+    ensure_conf_locked();
+    g_time_kernels = on ? 1 : 0;
+    pthread_mutex_unlock(&g_lock);
+}
+
 extern "C" void b200_spmv_set_auto_pin(int sightings)
 {
     pthread_mutex_lock(&g_lock);
     ensure_conf_locked();
     g_auto_pin = sightings > 0 ? sightings : 0;
     if (g_auto_pin == 0) {                       /* switched off: give everything back */
-        for (const RegSpan &sp : g_spans) { cudaHostUnregister(sp.lo); cudaGetLastError(); }
+        for (const RegSpan &sp : g_spans) { ++g_reg_events; cudaHostUnregister(sp.lo); cudaGetLastError(); }
         g_spans.clear();
         g_auto.clear();
     }
@@ -1065,6 +1101,7 @@ extern "C" int b200_spmv_unpin_host(void *ptr)
     pthread_mutex_lock(&g_lock);
     for (size_t i = 0; i < g_pinned.size(); ++i)
         if (g_pinned[i].lo == (char *)ptr) {
+            ++g_reg_events;
             cudaHostUnregister(ptr);
             g_pinned[i] = g_pinned.back();
             g_pinned.pop_back();

@@ -767,9 +767,9 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
     int launched_kernels = 1;
     if (m->kernel == B200_KERNEL_PANEL) {
         if (m->panel.fmt == 2) {
-            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull};
+            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull, 0};
             if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks;
-                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; }
+                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; xf.ready0 = sf->ready0; }
             XPush none;
             none.src = nullptr;
             const XPush &push = xp ? *xp : none;
@@ -778,9 +778,9 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
             else
                 launch_panelr<float>(m->panel, (const float *)d_x, (float *)d_y, xf, push, s);
         } else {
-            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull};
+            XFlags xf = {nullptr, 0ull, 1, 0, nullptr, 0ull, 0};
             if (sf) { xf.flags = sf->flags; xf.epoch = sf->epoch; xf.cols_per_rank = sf->cols_per_rank; xf.nranks = sf->nranks;
-                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; }
+                      xf.timed_out = sf->timed_out; xf.timeout_ns = sf->timeout_ns; xf.ready0 = sf->ready0; }
             if (m->dtype == B200_F64)
                 launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, s, nullptr, nullptr,
                                      xf.flags ? &xf : nullptr);
@@ -875,7 +875,7 @@ extern "C" int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y,
     if (!m) die("b200_spmv_exec_sliced: null matrix");
     if (!exec_takes_flags(m)) return -1;
     DeviceScope scope(m->device);
-    SliceFlags sf = {flags, epoch, cols_per_rank, nranks, nullptr, 0ull};
+    SliceFlags sf = {flags, epoch, cols_per_rank, nranks, nullptr, 0ull, 0};
     return exec_locked(m, d_x, d_y, (cudaStream_t)stream, &sf);
 }
 
@@ -900,7 +900,7 @@ extern "C" int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, vo
                                 &vflags, &cpr) != 0)
         return -1;
     DeviceScope scope(m->device);
-    SliceFlags sf = {vflags, epoch, cols_per_rank, xp.nranks, nullptr, 0ull};
+    SliceFlags sf = {vflags, epoch, cols_per_rank, xp.nranks, nullptr, 0ull, 0};
     return exec_locked(m, xbuf, d_y, (cudaStream_t)stream, &sf, &xp);
 }
 

@@ -100,6 +100,7 @@ struct SliceFlags {
     int nranks;
     int *timed_out;                     /* watchdog, see XFlags; NULL: none */
     unsigned long long timeout_ns;
+    int ready0;                         /* slices [0, ready0) are complete by stream order */
 };
 
 b200_matrix *upload_locked(DevCtx *ctx, const void *a, const int *rowstr, const int *colidx,

@@ -136,6 +136,7 @@ struct XFlags {
     int nranks;
     int *timed_out;                     /* watchdog (NULL: wait for ever): set to 1 when a slice did not */
     unsigned long long timeout_ns;      /* ... arrive within this time; the kernel then goes on regardless */
+    int ready0;                         /* slices [0, ready0) are in the buffer by stream order: never waited for */
 };
 /* The exchange fused into the product: the kernel's CTAs first store this rank's slice into
  * every rank's buffer of the epoch (NVLink peer stores), the last one publishes the epoch;

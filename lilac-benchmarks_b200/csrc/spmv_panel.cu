@@ -290,7 +290,7 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
      * just before the panel is requested.  XF is a template parameter: the kernel a caller
      * with x resident in HBM gets (XF = false) carries none of this state -- the class C
      * instance sits at its 128-register limit */
-    int x_ready = 0;
+    int x_ready = XF ? xf.ready0 : 0;
     auto issue_panel = [&](int p) {                       /* called by thread 0 only (TMA path) */
         const int cbase = p * W;
         const int cw = min(W, ncols - cbase);
@@ -451,7 +451,7 @@ void launch_panel(const DevPanel &pm, const T *x, T *y, cudaStream_t s, const T 
                   const XFlags *flags)
 {
     if (pm.nblk <= 0) return;
-    const XFlags none = {nullptr, 0ull, 1, 0, nullptr, 0ull};
+    const XFlags none = {nullptr, 0ull, 1, 0, nullptr, 0ull, 0};
     const XFlags &xf = flags ? *flags : none;
     const int threads = pm.R / pm.G;
     if (threads <= 256 && pm.U >= 5) {

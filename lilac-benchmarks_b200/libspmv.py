@@ -98,6 +98,8 @@ def lib():
     L.b200_spmv_reset_stats.argtypes = []
     L.b200_spmv_reset_stats.restype = None
     L.b200_spmv_set_auto_pin.argtypes = [c_int]
+    L.b200_spmv_set_time_kernels.argtypes = [c_int]
+    L.b200_spmv_set_time_kernels.restype = None
     L.b200_spmv_set_auto_pin.restype = None
     L.b200_spmv_pin_host.argtypes = [c_void_p, c_size_t]
     L.b200_spmv_pin_host.restype = c_int

@@ -1,6 +1,7 @@
 """Time the drop-in ABI call (host vectors) on one NPB class; library knobs come from the env.
 usage: [B200_SPMV_ZEROCOPY=0|1] [B200_SPMV_PIN_HOST=1] python scripts/e2e_probe.py C pinned|pageable|registered [iters]
 (registered: pageable numpy vectors handed to b200_spmv_pin_host, i.e. cudaHostRegister)"""
+import os
 import sys
 import time
 from pathlib import Path
@@ -44,6 +45,8 @@ for i in range(8):
     libspmv.spmv_harness(hy, m.a, hx[i & 3], m.rowstr, m.colidx, m.n)
     print(f"{cls} {mode}: call {i} done", file=sys.stderr, flush=True)
 libspmv.reset_stats()
+if os.environ.get('PROBE_TIME_KERNELS'):
+    libspmv.lib().b200_spmv_set_time_kernels(1)
 t0 = time.perf_counter()
 for i in range(iters):
     libspmv.spmv_harness(hy, m.a, hx[i & 3], m.rowstr, m.colidx, m.n)

@@ -1,12 +1,9 @@
+# one-off A/B of the drop-in path's x upload variants (scripts/e2e_probe.py), every step under a timeout
 P="python scripts/e2e_probe.py"
-run() { echo "== $*"; timeout ${TMO:-45} env "$@" 2>&1 | grep -v "^libb200\|call [1-7] done" | tail -4; echo "rc=${PIPESTATUS[0]}"; }
-TMO=150 run B200_X=1 $P C pinned 100
-run B200_X=1 $P C pageable 100
-run B200_SPMV_X_CHUNKS=1 $P C pageable 100
-run B200_SPMV_FLAG_WRITE=0 $P C pageable 100
-run B200_SPMV_X_PRELAUNCH=1 $P C pageable 100
-run B200_SPMV_X_PRELAUNCH=1 $P C pinned 100
-run B200_SPMV_X_OVERLAP=0 $P C pageable 100
-run B200_SPMV_X_OVERLAP=0 $P C pinned 100
-run B200_SPMV_PANEL_ROWS=512 $P C pageable 100
-run B200_X=1 $P B pageable 100
+run() { echo "== $*"; timeout ${TMO:-60} env "$@" 2>&1 | grep -v "^libb200-spmv: up\|call [0-7] done\|matrix ready" | tail -4; echo "rc=${PIPESTATUS[0]}"; }
+TMO=150 run B200_X=1 $P C pinned 300
+run B200_X=1 $P C pageable 300
+run B200_SPMV_PIN_HOST=3 $P C pageable 300
+run B200_SPMV_X_OVERLAP_AUTO=1 B200_SPMV_PIN_HOST=3 $P C pageable 300
+run B200_SPMV_X_OVERLAP=0 $P C pinned 300
+run B200_SPMV_X_OVERLAP=0 $P C pageable 300
