@@ -95,6 +95,7 @@ static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
 /* one device: x uploaded in chunks by the copy engine WHILE the product runs (the PANEL kernels
  * walk the columns left to right and wait per chunk) instead of in full before it */
 static int g_x_overlap = 1, g_x_chunks = 6, g_x_prelaunch = 0;
+static int g_x_second_early = 1;   /* ... and the second one requested before the launch */
 static int g_x_first_kernel = 1;   /* the first chunk by the PCIe-reading copy kernel on the product's stream */
 static int g_x_overlap_auto = 0;   /* experiment: overlap also for vectors this library registered */
 static int g_x_test_stall = 0;     /* test hook: the last chunk's flag of the next overlapped call is never written */
@@ -291,7 +292,8 @@ static void ensure_conf_locked(void)
     g_x_prelaunch = env_int("B200_SPMV_X_PRELAUNCH", 0);
     g_x_test_stall = env_int("B200_SPMV_X_TEST_STALL", 0);
     g_x_overlap_auto = env_int("B200_SPMV_X_OVERLAP_AUTO", 0);
-    g_x_first_kernel = env_int("B200_SPMV_X_FIRST_KERNEL", 1);      /* 1: every chunk is issued before the launch */
+    g_x_first_kernel = env_int("B200_SPMV_X_FIRST_KERNEL", 1);
+    g_x_second_early = env_int("B200_SPMV_X_SECOND_EARLY", 1);      /* 1: every chunk is issued before the launch */
     g_x_overlap_min = (size_t)std::max(0, env_int("B200_SPMV_X_OVERLAP_MIN_KB", 256)) << 10;
     if (g_x_overlap && env_int("B200_SPMV_FLAG_WRITE", 1)) {
         void *fn = nullptr;
@@ -899,7 +901,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         } else if (overlap) {
             /* with the first chunk on the product's stream, the second one (copy engine: ~20 us
              * from here to its flag) is requested before the launch as well */
-            x_sent = g_x_prelaunch ? e.x_nchunks : std::min(e.x_nchunks, first_by_kernel ? 2 : 1);
+            x_sent = g_x_prelaunch ? e.x_nchunks : std::min(e.x_nchunks, first_by_kernel && g_x_second_early ? 2 : 1);
             for (int k = 0; k < x_sent; ++k) send_chunk(k);
         } else if (bytes > 0) {
             if (g_zero_copy) {

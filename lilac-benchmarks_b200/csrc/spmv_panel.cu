@@ -42,6 +42,8 @@
  */
 #include "panel_common.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 /* ---- build: entries of every (row, panel) -------------------------------- */
@@ -264,6 +266,8 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = blockIdx.x;
+    /* a kernel behind this one in the stream may start its CTAs as ours finish (see below) */
+    asm volatile("griddepcontrol.launch_dependents;");
     const P2 *val2 = reinterpret_cast<const P2 *>(val);
     const uint32_t *col2 = reinterpret_cast<const uint32_t *>(col);
 
@@ -331,12 +335,6 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
         }
     };
 
-    if (use_tma) {
-        if (tid == 0) issue_panel(0);
-    } else {
-        coop_panel(0);
-    }
-
     /* request the first two chunks of the matrix stream */
     StreamCursor cur;
     {
@@ -348,6 +346,18 @@ spmv_panel_kernel(const T *__restrict__ val, const uint16_t *__restrict__ col,
     Chunk<T, U> a, b;
     cursor_load<T, U>(a, cur, val2, col2, s_slice, spb, warp, lane, P);
     cursor_load<T, U>(b, cur, val2, col2, s_slice, spb, warp, lane, P);
+
+    /* Everything above read only the resident matrix (immutable) and wrote only shared memory.
+     * Launched with programmatic stream serialisation (launch_panel_xf), this grid's CTAs
+     * take their SMs as the CTAs of the kernel in front of it in the stream finish one by
+     * one, do all of that -- table, sums, the first matrix chunks on their way -- and wait
+     * HERE for the rest of that kernel before they touch x or y.  (No-op otherwise.) */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (use_tma) {
+        if (tid == 0) issue_panel(0);
+    } else {
+        coop_panel(0);
+    }
 
     for (int p = 0; p < P; ++p) {
         /* double buffer: slot (p+1)&1 was released by the barrier that ended
@@ -433,6 +443,33 @@ static void launch_panel_xf(const DevPanel &pm, const T *x, T *y, const T *dotv,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const size_t smem = panel_smem_bytes(pm, sizeof(T) == 4);
     const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && pm.use_tma;
+    /* B200_SPMV_PDL (default 1): programmatic dependent launch -- back-to-back products (a
+     * CG loop, bench.py's timed steps) overlap one kernel's prologue with the tail of the one
+     * before.  Not while the stream is being captured into a graph. */
+    static int pdl = -1;
+    if (pdl < 0) { const char *v = getenv("B200_SPMV_PDL"); pdl = (v && *v) ? atoi(v) : 1; }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (pdl && (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) {
+        cudaGetLastError();
+        cap = cudaStreamCaptureStatusActive;
+    }
+    if (pdl && cap == cudaStreamCaptureStatusNone) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pm.nblk);
+        cfg.blockDim = dim3((unsigned)(pm.R / pm.G));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, spmv_panel_kernel<T, U, MAXT, XF>,
+                           static_cast<const T *>(pm.val), (const uint16_t *)pm.col, (const ushort4 *)pm.meta,
+                           (const int *)pm.slice_off, x, y, pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf,
+                           dotv, dot_partial, xf);
+        return;
+    }
     spmv_panel_kernel<T, U, MAXT, XF><<<pm.nblk, pm.R / pm.G, smem, s>>>(
         static_cast<const T *>(pm.val), pm.col, pm.meta, pm.slice_off, x, y,
         pm.rows, pm.ncols, pm.P, pm.W, pm.R, use_tma, pm.nbuf, dotv, dot_partial, xf);
