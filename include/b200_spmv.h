@@ -186,7 +186,7 @@ void b200_spmv_reset_stats(void);
 void b200_spmv_set_time_kernels(int on);
 
 /* Pin a caller-owned host vector so x / y move in place over PCIe instead of through the
- * library's pinned bounce buffer (class C: 0.15 ms per call instead of 0.29 ms).  Either the
+ * library's pinned bounce buffer (class C: 0.12 ms per call instead of 0.23 ms).  Either the
  * owner does it (b200_spmv_pin_host, or its own cudaHostAlloc / cudaHostRegister), or the
  * library does: with B200_SPMV_PIN_HOST=N / b200_spmv_set_auto_pin(N), N > 0, the drop-in
  * symbols register a vector once they have seen it N times at the same address (NPB's COMMON
