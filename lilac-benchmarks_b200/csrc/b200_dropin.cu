@@ -44,6 +44,9 @@
 
 #include <algorithm>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 using namespace b200;
 
@@ -97,6 +100,7 @@ static int g_zero_copy = 1, g_auto_pin = 0, g_guard = 1;
 static int g_x_overlap = 1, g_x_chunks = 6, g_x_prelaunch = 0;
 static int g_x_second_early = 1;   /* ... and the second one requested before the launch */
 static int g_x_first_kernel = 1;   /* the first chunk by the PCIe-reading copy kernel on the product's stream */
+static int g_nt_copy = 1;          /* non-temporal stores into the bounce buffer (copy_to_bounce) */
 static int g_x_overlap_auto = 0;   /* experiment: overlap also for vectors this library registered */
 static int g_x_test_stall = 0;     /* test hook: the last chunk's flag of the next overlapped call is never written */
 static size_t g_x_overlap_min = 256u << 10;
@@ -293,7 +297,8 @@ static void ensure_conf_locked(void)
     g_x_test_stall = env_int("B200_SPMV_X_TEST_STALL", 0);
     g_x_overlap_auto = env_int("B200_SPMV_X_OVERLAP_AUTO", 0);
     g_x_first_kernel = env_int("B200_SPMV_X_FIRST_KERNEL", 1);
-    g_x_second_early = env_int("B200_SPMV_X_SECOND_EARLY", 1);      /* 1: every chunk is issued before the launch */
+    g_x_second_early = env_int("B200_SPMV_X_SECOND_EARLY", 1);
+    g_nt_copy = env_int("B200_SPMV_NT_COPY", 1);      /* 1: every chunk is issued before the launch */
     g_x_overlap_min = (size_t)std::max(0, env_int("B200_SPMV_X_OVERLAP_MIN_KB", 256)) << 10;
     if (g_x_overlap && env_int("B200_SPMV_FLAG_WRITE", 1)) {
         void *fn = nullptr;
@@ -560,6 +565,38 @@ static void auto_pin_revoke(const void *p)
                                        "back to the bounce buffer\n", p);
         return;
     }
+}
+
+/* Caller vector -> pinned bounce buffer.  The destination is read next by the GPU (DMA or a
+ * PCIe-reading kernel), never by this CPU, so the stores bypass the cache: no read-for-ownership
+ * of lines the device fetched last call, no eviction of the caller's working set -- glibc's memcpy
+ * switches to such stores only far above these sizes.  Ends with a store fence: the data is
+ * globally visible before the copy that reads it is issued.  (B200_SPMV_NT_COPY=0: plain memcpy.) */
+static void copy_to_bounce(void *dst, const void *src, size_t n)
+{
+#if defined(__x86_64__)
+    if (g_nt_copy && n >= 4096) {
+        char *d = (char *)dst;
+        const char *s = (const char *)src;
+        const size_t head = (size_t)(-(intptr_t)d) & 15;          /* to a 16-byte destination boundary */
+        if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i v0 = _mm_loadu_si128((const __m128i *)(s + i));
+            const __m128i v1 = _mm_loadu_si128((const __m128i *)(s + i + 16));
+            const __m128i v2 = _mm_loadu_si128((const __m128i *)(s + i + 32));
+            const __m128i v3 = _mm_loadu_si128((const __m128i *)(s + i + 48));
+            _mm_stream_si128((__m128i *)(d + i), v0);
+            _mm_stream_si128((__m128i *)(d + i + 16), v1);
+            _mm_stream_si128((__m128i *)(d + i + 32), v2);
+            _mm_stream_si128((__m128i *)(d + i + 48), v3);
+        }
+        _mm_sfence();
+        if (i < n) memcpy(d + i, s + i, n - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
 }
 
 /* four sample positions (byte offsets, multiples of es) spread over [0, bytes) */
@@ -831,7 +868,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         x_pinned = (const char *)iv;
         if (!x_alias) {
             x_bounce = true;
-            if (!overlap) memcpy(e.h_x, iv, x_used);
+            if (!overlap) copy_to_bounce(e.h_x, iv, x_used);
             x_pinned = (const char *)e.h_x;
             x_alias = (const char *)e.h_x_alias;
         }
@@ -868,7 +905,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         Part &pt = e.part[0];
         const size_t lo = std::min(x_used, (size_t)k * e.x_chunk_cols * es);
         const size_t hi = std::min(x_used, (size_t)(k + 1) * e.x_chunk_cols * es);
-        if (hi > lo && x_bounce) memcpy((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
+        if (hi > lo && x_bounce) copy_to_bounce((char *)e.h_x + lo, (const char *)iv + lo, hi - lo);
         if (k == 0 && first_by_kernel) {
             void *dst[1] = {pt.d_x};
             if (hi > lo) launch_copy_in_multi(x_alias, dst, 1, hi - lo, pt.ctx->stream);
