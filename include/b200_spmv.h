@@ -93,11 +93,13 @@ void b200_spmv_release(b200_matrix *m);
  * d_x must hold at least b200_spmv_ncols(m) elements.  Asynchronous. */
 int b200_spmv_exec(b200_matrix *m, const void *d_x, void *d_y, void *stream);
 
-/* The same on x that is still being assembled from the slices of `nranks` GPUs
- * (include/b200_peer.h): flags[r] >= epoch <=> columns [r * cols_per_rank, (r + 1) *
- * cols_per_rank) are in d_x.  The kernel waits per slice, just before the panels that
- * need it, so the product overlaps the exchange.  Returns -1 without launching when the
- * matrix's kernel family cannot do that (wait for the vector first, then b200_spmv_exec). */
+/* The same on x that is still arriving slice by slice -- from `nranks` GPUs
+ * (include/b200_peer.h), or from the host through a copy engine (what the drop-in symbols
+ * do per call): flags[r] >= epoch <=> columns [r * cols_per_rank, (r + 1) * cols_per_rank)
+ * are in d_x.  The kernel waits per slice, just before the panels that need it, so the
+ * product overlaps the transfer.  Both PANEL kernels can (column panels walked left to
+ * right); returns -1 without launching for the other families (wait for the vector first,
+ * then b200_spmv_exec). */
 int b200_spmv_exec_sliced(b200_matrix *m, const void *d_x, void *d_y, void *stream,
                           const unsigned long long *flags, unsigned long long epoch,
                           int cols_per_rank, int nranks);
@@ -127,7 +129,7 @@ b200_matrix *b200_spmv_upload_device(const void *d_a, const int *d_rowstr, const
                                      int rows, int dtype, int kernel);
 
 int         b200_spmv_device(const b200_matrix *m);  /* device the matrix lives on */
-int         b200_spmv_waits_in_kernel(const b200_matrix *m);  /* 1: b200_spmv_exec_sliced works */
+int         b200_spmv_waits_in_kernel(const b200_matrix *m);  /* 1: the wide-matrix (ring) PANEL kernel: sliced and pushed products */
 int         b200_spmv_rows(const b200_matrix *m);
 int         b200_spmv_ncols(const b200_matrix *m);   /* max(colidx) */
 int64_t     b200_spmv_nnz(const b200_matrix *m);

@@ -16,13 +16,17 @@
  *                          freed and mapped again): a content fingerprint
  *                          checked on every call (B200_SPMV_VALIDATE=0: off) and
  *                          b200_spmv_invalidate().
- *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but pinned caller
- *                          vectors are read / written in place over PCIe by the
- *                          kernels, pageable ones go through pinned bounce buffers
- *                          (a pool of copy threads for the two memcpy's was measured
- *                          and dropped: waking sleeping helpers costs more than the
- *                          75 us copy, NPB CG class C went from 1.34 s to 2.06 s,
- *                          profiles/r02_run3_bench_C.json).
+ *   libspmv/gpu.c:264,285  x H2D and y D2H on every call: same, but on one device with a
+ *                          PANEL kernel x goes up WHILE the product runs -- first chunk by
+ *                          a PCIe-reading copy kernel on the product's stream, the others
+ *                          by the copy engine on a second stream, a flag per chunk, the
+ *                          kernel waits per chunk (watchdog on the wait; run_call) --,
+ *                          pageable vectors through pinned bounce buffers (non-temporal
+ *                          stores, chunk by chunk under the same overlap), and y is stored
+ *                          by the kernel straight into pinned memory.  (A pool of copy
+ *                          threads for the two memcpy's was measured and dropped: waking
+ *                          sleeping helpers costs more than the 75 us copy, NPB CG class C
+ *                          went from 1.34 s to 2.06 s, profiles/r02_run3_bench_C.json.)
  *   single device          gpu.c drives one GPU.  With B200_SPMV_DEVICES=0,1,..
  *                          (or "all") the SAME two symbols drive several: the rows
  *                          are split into nnz-balanced blocks, one per device;

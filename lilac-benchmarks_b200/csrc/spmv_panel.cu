@@ -39,6 +39,13 @@
  *
  * Algorithmic bytes are unchanged; the private layout streams
  * ~10 B per nonzero plus padding.
+ *
+ * Two things around the kernel proper.  (1) Programmatic dependent launch: the CTAs release
+ * their dependents at once and wait (griddepcontrol.wait) only after everything that reads
+ * nothing but the immutable matrix -- so back-to-back products overlap the tail of one
+ * with the head of the next (class C 74.0 -> 70.3 us).  (2) A flagged instance (template
+ * parameter XF) for x that is still on its way from the host or from other GPUs: thread 0
+ * waits for the chunks a panel needs just before it requests the panel's slice.
  */
 #include "panel_common.cuh"
 
