@@ -344,7 +344,8 @@ def run_one_gpu(args):
         """Untimed calls until the GPU, its copy engines and the PCIe link are in the state a caller
         in the middle of a solve sees (they ramp up over tens of milliseconds of traffic: the
         first few hundred calls after an idle period ran 20-30 us slower)."""
-        t_start, n = time.perf_counter(), 0
+        npb.time_spmv_calls(addr, y_np, hm.a, x_list, hm.rowstr, hm.colidx, hm.n, 3)   # the first call uploads
+        t_start, n = time.perf_counter(), 3
         while time.perf_counter() - t_start < seconds:
             npb.time_spmv_calls(addr, y_np, hm.a, x_list, hm.rowstr, hm.colidx, hm.n, 50)
             n += 50

@@ -186,6 +186,9 @@ void b200_spmv_reset_stats(void);
  * default -- two event records and a query per call are ~3 us of a 130 us call --;
  * B200_SPMV_TIME_KERNELS=1 or this switch turn it on. */
 void b200_spmv_set_time_kernels(int on);
+/* The copy the drop-in path uses from a pageable caller vector into its pinned bounce buffer
+ * (cache-bypassing stores + store fence; B200_SPMV_NT_COPY=0: memcpy).  Host only. */
+void b200_spmv_host_copy(void *dst, const void *src, size_t bytes);
 
 /* Pin a caller-owned host vector so x / y move in place over PCIe instead of through the
  * library's pinned bounce buffer (class C: 0.12 ms per call instead of 0.23 ms).  Either the

@@ -61,6 +61,24 @@ def test_partition_rows_skewed_and_empty(libspmv):
     assert list(libspmv.partition_rows(empty, 2)) == [0, 0, 0]
 
 
+def test_bounce_buffer_copy_matches_memcpy_for_every_alignment(libspmv):
+    """b200_spmv_host_copy (cache-bypassing stores, head / 64-byte body / tail): every
+    source and destination alignment, sizes around the thresholds; bytes next to the
+    destination stay untouched."""
+    L = libspmv.lib()
+    L.b200_spmv_host_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.b200_spmv_host_copy.restype = None
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 256, 1 << 17, dtype=np.uint8)
+    for n in (0, 1, 63, 64, 4095, 4096, 4097, 4096 + 63, 8192 + 17, 100000):
+        for so in (0, 1, 7, 8, 15, 16, 33):
+            for do in (0, 1, 5, 8, 15, 16, 47):
+                dst = np.full(n + 128, 0xAB, dtype=np.uint8)
+                L.b200_spmv_host_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
+                assert np.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
+                assert np.all(dst[:do] == 0xAB) and np.all(dst[do + n:] == 0xAB), (n, so, do)
+
+
 def test_version_string(libspmv):
     assert b"sm_100a" in libspmv.lib().b200_spmv_version()
 

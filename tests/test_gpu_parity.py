@@ -972,3 +972,32 @@ def test_product_that_never_gets_its_chunk_times_out_and_is_redone(tmp_path):
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0 and "watchdog ok" in proc.stdout, proc.stdout[-3000:]
+
+
+def test_vector_pinned_at_both_ends_with_a_pageable_hole_takes_the_bounce_buffer(libspmv, oracle, npb):
+    """Two registrations can sit at the two ends of a vector whose middle is pageable
+    (neighbouring vectors registered page by page): first and last byte are pinned and their
+    device addresses are the right distance apart, yet a kernel or a copy engine reading the
+    range in place would fault.  The range check walks the registrations (b200_dropin.cu,
+    pinned_device_alias)."""
+    m = npb.NpbMatrix("W")
+    rng = np.random.default_rng(16)
+    buf = rng.standard_normal(m.n + 2 + 2048)
+    base = buf.ctypes.data
+    lo = (base + 4095) // 4096 * 4096
+    first = (lo - base) // 8
+    xv = buf[first:first + m.n + 2]
+    npages = (xv.nbytes + 4095) // 4096
+    assert xv.ctypes.data == lo and npages >= 6
+    tail = lo + (npages - 2) * 4096                      # the last two pages the vector touches
+    assert libspmv.lib().b200_spmv_pin_host(lo, 2 * 4096) == 0
+    assert libspmv.lib().b200_spmv_pin_host(tail, 2 * 4096) == 0
+    try:
+        y = np.zeros(m.n)
+        for _ in range(2):
+            xv[:] = rng.standard_normal(len(xv))
+            libspmv.spmv_harness(y, m.a, xv, m.rowstr, m.colidx, m.n)
+            assert np.array_equal(y, oracle.spmv(m.a, xv, m.rowstr, m.colidx))
+    finally:
+        assert libspmv.lib().b200_spmv_unpin_host(lo) == 0
+        assert libspmv.lib().b200_spmv_unpin_host(tail) == 0
