@@ -10,6 +10,8 @@
 #   sweep TAG SHAPE "cfg,cfg,..." [iters] [graph]   scripts/sweep.py (kernel-only timing of layouts; "graph": one CUDA graph replay)
 #   launches TAG [bench.py args]              ncu launch list (gpu__time_duration) of a short bench run
 #   ncufull TAG KERNEL_REGEX CMD...           one ncu --set full capture (+ raw/source CSV, stall summary)
+#   e2e TAG CLASS MODE "ENV=V ENV=V|..." [calls]   scripts/e2e_probe.py (drop-in call, C caller loop, steady state) once per
+#                                             "|"-separated set of environment assignments, each run under a timeout
 #   smoke                                     __graft_entry__.smoke()
 set -u
 mkdir -p gpurun_out
@@ -46,6 +48,15 @@ ncufull)
     ncu -i gpurun_out/$tag.ncu-rep --page source --csv > gpurun_out/${tag}_src.csv 2>/dev/null
     python scripts/ncu_stalls.py gpurun_out/${tag}_src.csv 25 > gpurun_out/${tag}_stalls.txt 2>&1
     head -12 gpurun_out/${tag}_stalls.txt ;;
+e2e)
+    tag=$1; cls=$2; mode=$3; sets=${4:-}; calls=${5:-300}
+    IFS='|' read -ra variants <<< "${sets:-B200_X=1}"
+    for v in "${variants[@]}"; do
+        echo "== $v" | tee -a gpurun_out/$tag.txt
+        # shellcheck disable=SC2086
+        timeout 150 env $v python scripts/e2e_probe.py "$cls" "$mode" "$calls" 2>&1 \
+            | grep -v "^libb200-spmv: up\|matrix ready" | tail -3 | tee -a gpurun_out/$tag.txt
+    done ;;
 smoke)
     timeout 600 python -c "import __graft_entry__ as e; e.smoke()" ;;
 *)
