@@ -835,10 +835,12 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
     if (y_auto) sample_offsets((size_t)n * es, es, y_off);
 
     const bool multi = e.nparts > 1;
-    /* One device and a kernel that walks the columns left to right (PANEL, RING): x goes up in
-     * chunks through the copy engine on a second stream WHILE the product runs; the kernel
-     * waits per chunk just before the panels that need it (XFlags).  The first chunk is issued
-     * before the launch, the others after it, so the product starts ~10 us into the call
+    /* One device and the paired PANEL kernel (it walks the columns left to right, and its
+     * flagged instance has a watchdog on the wait): x goes up in chunks WHILE the product runs
+     * -- the first by a copy kernel on the product's stream, the others through the copy engine
+     * on a second stream --; the kernel waits per chunk just before the panels that need it
+     * (XFlags).  The first two chunks are requested before the launch, the others after it,
+     * so the product starts ~10 us into the call
      * instead of after the whole vector has crossed PCIe -- and for a pageable vector the
      * memcpy into the bounce buffer overlaps the product chunk by chunk as well.
      * (The other way round -- the product kernel fetching x itself over PCIe, chunk by chunk
