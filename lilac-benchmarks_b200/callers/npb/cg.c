@@ -198,3 +198,9 @@ double npb_time_spmv_calls(spmv_harness_fn harness, double *ov, double *a, doubl
     for (int i = 0; i < calls; ++i) harness(ov, a, xs[i % nx], rowstr, colidx, &n);
     return wtime() - t0;
 }
+
+void npb_issue_exec_calls(spmv_exec_fn exec, void *matrix, void *const *d_xs, int nx, void *d_y,
+                          void *stream, int calls)
+{
+    for (int i = 0; i < calls; ++i) exec(matrix, d_xs[i % nx], d_y, stream);
+}

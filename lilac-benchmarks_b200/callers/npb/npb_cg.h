@@ -94,6 +94,15 @@ void npb_conj_grad(const npb_csr *m, spmv_harness_fn harness,
 double npb_time_spmv_calls(spmv_harness_fn harness, double *ov, double *a, double *const *xs, int nx,
                            int *rowstr, int *colidx, int rows, int calls);
 
+/* The same for a device-resident caller: `calls` back-to-back launches through the
+ * resident-matrix entry point (b200_spmv_exec: matrix handle, device x, device y, stream),
+ * x rotating over nx device vectors.  Launches only -- the caller brackets the loop with
+ * events on `stream` and synchronises.  (A scripting-language loop cannot issue launches
+ * faster than one per ~10 us, which hides kernels of a few microseconds.) */
+typedef int (*spmv_exec_fn)(void *matrix, const void *d_x, void *d_y, void *stream);
+void npb_issue_exec_calls(spmv_exec_fn exec, void *matrix, void *const *d_xs, int nx, void *d_y,
+                          void *stream, int calls);
+
 double npb_randlc(double *x, double a);
 
 #ifdef __cplusplus

@@ -201,6 +201,11 @@ def harness_address(f32=False):
     return C.cast(fn, c_void_p).value
 
 
+def exec_address():
+    """Address of b200_spmv_exec (what a C caller of the resident-matrix API binds)."""
+    return C.cast(lib().b200_spmv_exec, c_void_p).value
+
+
 def stats():
     s = Stats()
     lib().b200_spmv_get_stats(C.byref(s))
@@ -287,6 +292,11 @@ class ResidentMatrix:
         returns -1 without launching if this matrix's kernel cannot wait in-kernel."""
         return lib().b200_spmv_exec_sliced(self._h, c_void_p(d_x), c_void_p(d_y), c_void_p(stream),
                                            c_void_p(flags), int(epoch), int(cols_per_rank), int(nranks))
+
+    @property
+    def handle(self):
+        """The b200_matrix* as an int (for C callers of the resident-matrix API)."""
+        return int(self._h)
 
     def exec_ptr(self, d_x, d_y, stream=0):
         """Launch on raw device pointers (ints) and a cudaStream_t handle (int)."""

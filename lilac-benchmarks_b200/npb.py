@@ -53,6 +53,8 @@ def lib():
                                           POINTER(POINTER(c_double)), c_int, POINTER(c_int),
                                           POINTER(c_int), c_int, c_int]
         L.npb_time_spmv_calls.restype = c_double
+        L.npb_issue_exec_calls.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int]
+        L.npb_issue_exec_calls.restype = None
         L.npb_vectors_get.argtypes = [POINTER(CgClass), POINTER(c_void_p), POINTER(c_void_p),
                                       POINTER(c_void_p), POINTER(c_void_p)]
         L.npb_vectors_get.restype = c_int
@@ -204,6 +206,15 @@ def run_cg(matrix, harness_addr, verbose=False):
     return {"zeta": res.zeta, "rnorm": res.rnorm, "err": res.err, "verified": bool(res.verified),
             "t_bench": res.t_bench, "t_init": res.t_init, "mops": res.mops,
             "spmv_calls": res.spmv_calls, "zeta_hist": zeta_hist, "rnorm_hist": rnorm_hist}
+
+
+def issue_exec_calls(exec_addr, matrix_handle, d_xs, d_y, stream, calls):
+    """`calls` back-to-back launches of the resident product issued by the C loop
+    npb_issue_exec_calls (callers/npb/cg.c): `exec_addr` is the address of b200_spmv_exec,
+    `d_xs` device pointers (ints) the x argument rotates over.  No synchronisation."""
+    arr = (c_void_p * len(d_xs))(*[c_void_p(int(p)) for p in d_xs])
+    lib().npb_issue_exec_calls(c_void_p(exec_addr), c_void_p(matrix_handle), arr, len(d_xs), c_void_p(int(d_y)),
+                               c_void_p(int(stream)), int(calls))
 
 
 def time_spmv_calls(harness_addr, ov, a, xs, rowstr, colidx, rows, calls):

@@ -7,7 +7,7 @@
 #   test [pytest -k expr]                     pytest -m gpu
 #   bench TAG [bench.py args]                 one-GPU bench line
 #   benchn N TAG [bench.py args]              N ranks under torch.distributed.run
-#   sweep TAG SHAPE "cfg,cfg,..." [iters] [graph]   scripts/sweep.py (kernel-only timing of layouts; "graph": one CUDA graph replay)
+#   sweep TAG SHAPE "cfg,cfg,..." [iters] [graph|cloop]   scripts/sweep.py (kernel-only timing of layouts; "graph": one CUDA graph replay, "cloop": launches from a C loop)
 #   launches TAG [bench.py args]              ncu launch list (gpu__time_duration) of a short bench run
 #   ncufull TAG KERNEL_REGEX CMD...           one ncu --set full capture (+ raw/source CSV, stall summary)
 #   e2e TAG CLASS MODE "ENV=V ENV=V|..." [calls]   scripts/e2e_probe.py (drop-in call, C caller loop, steady state) once per

@@ -1,7 +1,9 @@
 """Kernel-only timing sweep over panel geometry / kernel family on one NPB class.
 usage: python scripts/sweep.py C "16384x1024,8192x512,ordered,vector" [iters] [graph]
 "graph": the launches are captured in one CUDA graph and the replay is timed -- for kernels of a
-few microseconds, which a Python loop of ctypes calls (~10 us per launch) cannot issue fast enough."""
+few microseconds, which a Python loop of ctypes calls (~10 us per launch) cannot issue fast enough.
+"cloop": the launches are issued by the C loop of callers/npb (npb_issue_exec_calls): plain stream
+launches as a compiled device-resident caller makes them, dependent launches included."""
 import os
 import sys
 import time
@@ -21,6 +23,7 @@ cls = sys.argv[1] if len(sys.argv) > 1 else "C"
 configs = (sys.argv[2] if len(sys.argv) > 2 else "16384x1024,ordered,vector").split(",")
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 use_graph = len(sys.argv) > 4 and sys.argv[4] == "graph"
+use_cloop = len(sys.argv) > 4 and sys.argv[4] == "cloop"      # launches issued by callers/npb's C loop
 if cls.startswith("crsmat"):
     from lilac_benchmarks_b200 import gen
 
@@ -101,6 +104,13 @@ for cfg_full in configs:
         torch.cuda.synchronize()
         e0.record()
         g.replay()
+        e1.record()
+    elif use_cloop:
+        stream = torch.cuda.current_stream().cuda_stream
+        npb.issue_exec_calls(libspmv.exec_address(), rm.handle, [v.data_ptr() for v in xs], y.data_ptr(), stream, iters)
+        torch.cuda.synchronize()
+        e0.record()
+        npb.issue_exec_calls(libspmv.exec_address(), rm.handle, [v.data_ptr() for v in xs], y.data_ptr(), stream, iters)
         e1.record()
     else:
         e0.record()
