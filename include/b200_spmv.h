@@ -65,9 +65,12 @@ enum {
                                  x slices staged in shared memory (sorted rows) */
     B200_KERNEL_MERGE   = 4,  /* fixed-nnz split with carry-out fix-up for
                                  heavily skewed row lengths */
-    B200_KERNEL_SELL    = 5   /* lane streams over the sorted-SELL private layout,
+    B200_KERNEL_SELL    = 5,  /* lane streams over the sorted-SELL private layout,
                                  x gathered through L2; left-to-right rows for any
                                  column order (wide matrices, unsorted rows) */
+    B200_KERNEL_SMALL   = 6   /* small matrices: the whole x in shared memory, one
+                                 nnz-balanced row block per SM, products staged, one
+                                 thread per row adds left to right (any column order) */
 };
 
 enum { B200_F64 = 0, B200_F32 = 1 };

@@ -132,6 +132,7 @@ static int kernel_from_env(int requested)
     if (!strcmp(v, "panel")) return B200_KERNEL_PANEL;
     if (!strcmp(v, "merge")) return B200_KERNEL_MERGE;
     if (!strcmp(v, "sell")) return B200_KERNEL_SELL;
+    if (!strcmp(v, "small")) return B200_KERNEL_SMALL;
     if (!strcmp(v, "auto")) return B200_KERNEL_AUTO;
     die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|sell|merge", v);
     return 0;
@@ -605,6 +606,55 @@ static bool build_sell_locked(b200_matrix *m, const int *rowstr, bool all_rows_s
     return true;
 }
 
+/* SMALL: x (ncols elements) and a tile of products must share one SM's shared memory, and
+ * the nnz-balanced row blocks must form ONE wave (one CTA per SM).  The tile grows from
+ * nnz / SMs until the greedy blocks fit the SM count; a row longer than the tile rules the
+ * family out (the panel kernels take such matrices). */
+static bool build_small_locked(b200_matrix *m, const int *rowstr)
+{
+    if (m->rows <= 0 || m->nnz <= 0 || m->ncols <= 0) return false;
+    const size_t es = elem_size(m->dtype);
+    const int xpad = (m->ncols + 3) & ~3;
+    const size_t x_bytes = (size_t)xpad * es;
+    if (x_bytes + 4096 > kSmemMax) return false;
+    const long long cap = (long long)((kSmemMax - x_bytes - 256) / es);
+    const int sms = m->ctx->sm_count;
+    long long tile = std::max<long long>((m->nnz + sms - 1) / sms, m->scan.max_len);
+    tile = std::max<long long>(tile, 64);
+    std::vector<int> blk;
+    for (;;) {
+        if (tile > cap) return false;
+        blk.clear();
+        blk.push_back(0);
+        int r = 0;
+        bool ok = true;
+        while (r < m->rows) {
+            long long used = 0;
+            const int start = r;
+            while (r < m->rows) {
+                const long long len = (long long)rowstr[r + 1] - rowstr[r];
+                if (used + len > tile) break;
+                used += len;
+                ++r;
+            }
+            if (r == start) { ok = false; break; }         /* a row longer than the tile */
+            blk.push_back(r);
+        }
+        if (ok && (int)blk.size() - 1 <= sms) break;
+        if (tile == cap) return false;
+        tile = std::min<long long>(cap, tile + std::max<long long>(tile / 64, 8));
+    }
+    CUDA_OK(cudaMalloc((void **)&m->d_small_blk, blk.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(m->d_small_blk, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m->small_.rowblk = m->d_small_blk;
+    m->small_.nblk = (int)blk.size() - 1;
+    m->small_.tile = (int)tile;
+    m->small_.xpad = xpad;
+    m->small_.ncols = m->ncols;
+    m->resident_bytes += (int64_t)(blk.size() * sizeof(int));
+    return true;
+}
+
 namespace b200 {
 
 /* `on_device`: a / rowstr / colidx are DEVICE arrays of m's device (same 1-based
@@ -701,6 +751,11 @@ static b200_matrix *upload_any_locked(DevCtx *ctx, const void *a, const int *row
 
     /* kernel choice from the histogram */
     kernel = kernel_from_env(kernel);
+    /* the launch-bound regime first: x and one SM's share of the products in shared memory */
+    if (kernel == B200_KERNEL_SMALL || (kernel == B200_KERNEL_AUTO && env_int("B200_SPMV_SMALL", 1))) {
+        if (build_small_locked(m, rowstr)) kernel = B200_KERNEL_SMALL;
+        else if (kernel == B200_KERNEL_SMALL) kernel = B200_KERNEL_AUTO;
+    }
     if (kernel == B200_KERNEL_AUTO || kernel == B200_KERNEL_PANEL) {
         if (build_panel_locked(m, kernel == B200_KERNEL_PANEL)) kernel = B200_KERNEL_PANEL;
         else kernel = B200_KERNEL_SELL;
@@ -740,6 +795,7 @@ void release_locked(b200_matrix *m)
     cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
     cudaFree(m->d_scol); cudaFree(m->d_chunks); cudaFree(m->d_multi); cudaFree(m->d_multi_rows);
     cudaFree(m->d_carry);
+    cudaFree(m->d_small_blk);
     free(m);
 }
 
@@ -788,6 +844,11 @@ int exec_locked(b200_matrix *m, const void *d_x, void *d_y, cudaStream_t s, cons
                 launch_panel<float>(m->panel, (const float *)d_x, (float *)d_y, s, nullptr, nullptr,
                                     xf.flags ? &xf : nullptr);
         }
+    } else if (m->kernel == B200_KERNEL_SMALL) {
+        if (m->dtype == B200_F64)
+            launch_small<double>(m->small_, m->dev, (const double *)d_x, (double *)d_y, s);
+        else
+            launch_small<float>(m->small_, m->dev, (const float *)d_x, (float *)d_y, s);
     } else if (m->kernel == B200_KERNEL_SELL || m->kernel == B200_KERNEL_MERGE) {
         if (m->dtype == B200_F64)
             launch_sell<double>(m->sell, m->dev, (const double *)d_x, (double *)d_y, s);
@@ -944,6 +1005,7 @@ extern "C" const char *b200_spmv_kernel_name(const b200_matrix *m)
     case B200_KERNEL_PANEL:   return "panel";
     case B200_KERNEL_MERGE:   return "merge";
     case B200_KERNEL_SELL:    return "sell";
+    case B200_KERNEL_SMALL:   return "small";
     default: return "auto";
     }
 }

@@ -86,6 +86,9 @@ struct b200_matrix {
     void *d_pval; uint16_t *d_pcol; ushort4 *d_meta; int *d_slice_off;
     /* SELL layout (when kernel == B200_KERNEL_SELL) */
     b200::DevSell sell;
+    /* SMALL (when kernel == B200_KERNEL_SMALL): the CSR arrays above + its own row blocks */
+    b200::DevSmall small_;
+    int *d_small_blk;
     int *d_scol; int4 *d_chunks; int2 *d_multi; int *d_multi_rows; void *d_carry;
 };
 

@@ -52,6 +52,17 @@ void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
 
 int tile_elems(bool f32);
 
+/* SMALL: whole x in shared memory, one nnz-balanced row block per SM (spmv_kernels.cu) */
+struct DevSmall {
+    const int *rowblk;    /* int[nblk + 1], first row of every row block */
+    int nblk;
+    int tile;             /* products a CTA can hold (entries) */
+    int xpad;             /* elements reserved for x in shared memory */
+    int ncols;
+};
+template <typename T>
+void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s);
+
 /* dst[0..bytes) = src[0..bytes): src is a device alias of pinned host memory,
  * so the loads travel over PCIe; runs on the SMs, in stream order */
 void launch_copy_in(const void *src, void *dst, size_t bytes, cudaStream_t s);

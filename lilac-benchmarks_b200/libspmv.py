@@ -17,7 +17,7 @@ import numpy as np
 from .build import B200_SO
 
 KERNEL_AUTO, KERNEL_ORDERED, KERNEL_VECTOR, KERNEL_PANEL, KERNEL_MERGE = range(5)
-KERNEL_IDS = {"auto": 0, "ordered": 1, "vector": 2, "panel": 3, "merge": 4, "sell": 5}
+KERNEL_IDS = {"auto": 0, "ordered": 1, "vector": 2, "panel": 3, "merge": 4, "sell": 5, "small": 6}
 F64, F32 = 0, 1
 
 

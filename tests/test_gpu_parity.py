@@ -900,7 +900,7 @@ for cls, fmt in (("W", None), ("A", None), ("A", "2")):
     os.environ.pop("B200_SPMV_PANEL_FMT", None)
 # the sliced entry point on the paired layout, x NOT 16-byte aligned (cooperative slice loads)
 m = npb.NpbMatrix("W")
-rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel="panel")
 assert rm.kernel_name == "panel"
 xh = rng.standard_normal(m.n + 3)
 xd = torch.from_numpy(xh).cuda()
@@ -930,7 +930,8 @@ def test_x_uploaded_in_chunks_while_the_product_runs(tmp_path, chunks, flag_writ
     script = tmp_path / "overlap.py"
     script.write_text(OVERLAP_SCRIPT.format(root=root))
     env = dict(os.environ, B200_SPMV_X_OVERLAP_MIN_KB="0", B200_SPMV_X_CHUNKS=str(chunks),
-               B200_SPMV_FLAG_WRITE=str(flag_write), B200_SPMV_GUARD="0")
+               B200_SPMV_FLAG_WRITE=str(flag_write), B200_SPMV_GUARD="0",
+               B200_SPMV_SMALL="0")          # the classes used here are small enough for the SMALL family
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0 and "overlap ok" in proc.stdout, proc.stdout[-3000:]
@@ -968,7 +969,7 @@ def test_product_that_never_gets_its_chunk_times_out_and_is_redone(tmp_path):
     script = tmp_path / "watchdog.py"
     script.write_text(WATCHDOG_SCRIPT.format(root=root))
     env = dict(os.environ, B200_SPMV_X_OVERLAP_MIN_KB="0", B200_SPMV_X_CHUNKS="4", B200_SPMV_X_TEST_STALL="1",
-               B200_SPMV_X_TIMEOUT_MS="5")
+               B200_SPMV_X_TIMEOUT_MS="5", B200_SPMV_SMALL="0")
     proc = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0 and "watchdog ok" in proc.stdout, proc.stdout[-3000:]
@@ -1001,3 +1002,44 @@ def test_vector_pinned_at_both_ends_with_a_pageable_hole_takes_the_bounce_buffer
     finally:
         assert libspmv.lib().b200_spmv_unpin_host(lo) == 0
         assert libspmv.lib().b200_spmv_unpin_host(tail) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("sort", [True, False])
+@pytest.mark.parametrize("shape", [
+    dict(n=1, ncols=1, mean=1, fits=True), dict(n=33, ncols=70, mean=9, fits=True),
+    dict(n=1000, ncols=1000, mean=25, fits=True), dict(n=5000, ncols=12000, mean=130, fits=True),
+    dict(n=14000, ncols=14000, mean=132, fits=True),        # NPB class A's shape
+    dict(n=150, ncols=9000, mean=2500, fits=True),          # few long rows
+    dict(n=20000, ncols=13000, mean=1, fits=True),          # mostly empty rows, base offset below
+    dict(n=3000, ncols=70000, mean=60, fits=False),         # x does not fit: falls back
+    dict(n=40, ncols=5000, mean=60000, fits=False),         # rows longer than any tile: falls back
+])
+def test_small_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape):
+    """SMALL family (whole x in shared memory, products staged per row block, one thread per
+    row adds left to right): bit-identical to the reference loop for sorted, unsorted and
+    repeated columns, empty rows, a row offset base > 1; matrices it cannot hold fall back to
+    the automatic choice."""
+    rng = np.random.default_rng(shape["n"] * 13 + shape["mean"])
+    lens = rng.poisson(shape["mean"], shape["n"])
+    lens[rng.random(shape["n"]) < 0.1] = 0
+    a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=sort,
+                               base=1 if shape["n"] < 1000 else 4)
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "small")
+    assert (m.kernel_name == "small") == shape["fits"], (m.kernel_name, m.ncols, m.nnz)
+    assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
+    m.release()
+
+
+def test_small_family_is_the_automatic_choice_for_npb_class_a(libspmv, oracle, npb):
+    import torch
+    m = npb.NpbMatrix("A")
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx)
+    assert rm.kernel_name == "small"
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(m.n + 2)
+    dy = torch.zeros(m.n, dtype=torch.float64, device="cuda")
+    for _ in range(3):                                   # back to back: dependent launches
+        rm.exec(torch.from_numpy(x).cuda(), dy)
+    assert np.array_equal(dy.cpu().numpy(), oracle.spmv(m.a, x, m.rowstr, m.colidx))
+    rm.release()
