@@ -651,6 +651,20 @@ static bool build_small_locked(b200_matrix *m, const int *rowstr)
     m->small_.tile = (int)tile;
     m->small_.xpad = xpad;
     m->small_.ncols = m->ncols;
+    m->small_.use_tma = env_int("B200_SPMV_SMALL_TMA", 1);
+    m->small_.pdl = env_int("B200_SPMV_PDL", 1);
+    m->small_.cfg = env_int("B200_SPMV_SMALL_CFG", 0);
+    m->small_.col16 = nullptr;
+    if (env_int("B200_SPMV_SMALL_COL16", 1)) {
+        /* fewer than 65 536 columns (x fits shared memory): 10 instead of 12 bytes per entry */
+        const size_t n16 = (size_t)m->nnz + kPadElems;
+        CUDA_OK(cudaMalloc((void **)&m->d_small_col16, n16 * sizeof(uint16_t)));
+        launch_small_col16(m->d_col, m->d_small_col16, n16, m->ctx->stream);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(m->ctx->stream));
+        m->small_.col16 = m->d_small_col16;
+        m->resident_bytes += (int64_t)(n16 * sizeof(uint16_t));
+    }
     m->resident_bytes += (int64_t)(blk.size() * sizeof(int));
     return true;
 }
@@ -795,7 +809,7 @@ void release_locked(b200_matrix *m)
     cudaFree(m->d_pval); cudaFree(m->d_pcol); cudaFree(m->d_meta); cudaFree(m->d_slice_off);
     cudaFree(m->d_scol); cudaFree(m->d_chunks); cudaFree(m->d_multi); cudaFree(m->d_multi_rows);
     cudaFree(m->d_carry);
-    cudaFree(m->d_small_blk);
+    cudaFree(m->d_small_blk); cudaFree(m->d_small_col16);
     free(m);
 }
 

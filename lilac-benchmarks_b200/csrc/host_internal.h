@@ -88,7 +88,7 @@ struct b200_matrix {
     b200::DevSell sell;
     /* SMALL (when kernel == B200_KERNEL_SMALL): the CSR arrays above + its own row blocks */
     b200::DevSmall small_;
-    int *d_small_blk;
+    int *d_small_blk; uint16_t *d_small_col16;
     int *d_scol; int4 *d_chunks; int2 *d_multi; int *d_multi_rows; void *d_carry;
 };
 

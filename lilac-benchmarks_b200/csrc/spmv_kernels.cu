@@ -145,110 +145,6 @@ void launch_ordered(const DevCsr &m, const T *x, T *y, cudaStream_t s)
 template void launch_ordered<double>(const DevCsr &, const double *, double *, cudaStream_t);
 template void launch_ordered<float>(const DevCsr &, const float *, float *, cudaStream_t);
 
-/* ------------------------------------------------------------------------
- * SMALL: the whole x in shared memory, one row block per SM
- *
- * For matrices that sit in L2 and whose x fits one SM's shared memory beside a tile of
- * products (NPB classes S, W, A; parboil's and bfs's inputs): the launch-bound regime, where
- * a kernel is as fast as its longest dependent chain.  ORDERED's two phases, sized for one
- * wave: (1) all 1024 threads compute the products of the CTA's nnz-balanced row block --
- * coalesced loads of the CSR arrays as uploaded, x gathered from shared memory -- into a
- * shared-memory tile; (2) one thread per row adds its products left to right.  The memory
- * phase runs with every warp of the SM, only the additions are serial, and their chain is the
- * longest row -- against one lane walking loads, gathers and additions of a whole row in the
- * panel kernels.  Same operations in the same order as native-impl.c:1-12 for ANY column
- * order.  Programmatic dependent launch like the PANEL kernel: the first batch of the matrix
- * stream is requested before griddepcontrol.wait.
- * ---------------------------------------------------------------------- */
-template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-spmv_small_kernel(const T *__restrict__ val, const int *__restrict__ col,
-                  const int *__restrict__ rowptr, const int *__restrict__ rowblk,
-                  const T *__restrict__ x, T *__restrict__ y, int ncols, int xpad)
-{
-    extern __shared__ __align__(16) unsigned char small_smem[];
-    T *xs = reinterpret_cast<T *>(small_smem);
-    T *prod = xs + xpad;
-    constexpr int U = 4;
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int tid = threadIdx.x;
-    const int r0 = __ldg(rowblk + blockIdx.x), r1 = __ldg(rowblk + blockIdx.x + 1);
-    const int lo = __ldg(rowptr + r0), n = __ldg(rowptr + r1) - lo;
-    const T *v_ = val + lo;
-    const int *c_ = col + lo;
-
-    T v[U];
-    int c[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {                 /* first batch: the matrix is immutable */
-        const int i = min(tid + u * THREADS, max(n - 1, 0));
-        v[u] = n > 0 ? ld_stream(v_ + i) : (T)0;
-        c[u] = n > 0 ? ld_stream(c_ + i) : 1;
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int i = tid; i < ncols; i += THREADS) xs[i] = __ldcg(x + i);
-    __syncthreads();
-    for (int i0 = tid; i0 < n; i0 += THREADS * U) {
-        if (i0 != tid) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = min(i0 + u * THREADS, n - 1);
-                v[u] = ld_stream(v_ + i);
-                c[u] = ld_stream(c_ + i);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * THREADS;
-            if (i < n) prod[i] = mul_rn(v[u], xs[c[u] - 1]);
-        }
-    }
-    __syncthreads();
-    for (int r = r0 + tid; r < r1; r += THREADS) {
-        const int s = __ldg(rowptr + r) - lo, e = __ldg(rowptr + r + 1) - lo;
-        T acc = (T)0;
-#pragma unroll 8
-        for (int k = s; k < e; ++k) acc = add_rn(acc, prod[k]);
-        y[r] = acc;
-    }
-}
-
-template <typename T>
-void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s)
-{
-    if (sm.nblk <= 0) return;
-    constexpr int THREADS = 1024;
-    static unsigned attr_set = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(attr_set & (1u << (dev & 31)))) {
-        attr_set |= 1u << (dev & 31);
-        cudaFuncSetAttribute(spmv_small_kernel<T, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    }
-    const size_t smem = ((size_t)sm.xpad + (size_t)sm.tile) * sizeof(T);
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
-    if (cap == cudaStreamCaptureStatusNone) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)sm.nblk);
-        cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, spmv_small_kernel<T, THREADS>, static_cast<const T *>(m.val), (const int *)m.col,
-                           (const int *)m.rowptr, (const int *)sm.rowblk, x, y, sm.ncols, sm.xpad);
-        return;
-    }
-    spmv_small_kernel<T, THREADS><<<sm.nblk, THREADS, smem, s>>>(static_cast<const T *>(m.val), m.col, m.rowptr,
-                                                               sm.rowblk, x, y, sm.ncols, sm.xpad);
-}
-template void launch_small<double>(const DevSmall &, const DevCsr &, const double *, double *, cudaStream_t);
-template void launch_small<float>(const DevSmall &, const DevCsr &, const float *, float *, cudaStream_t);
-
 int tile_elems(bool f32) { return f32 ? kTileF32 : kTileF64; }
 
 /* ------------------------------------------------------------------------

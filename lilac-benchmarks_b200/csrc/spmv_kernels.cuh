@@ -52,14 +52,19 @@ void launch_upload_scan(const int *rowptr, const int *col, int rows, int nnz,
 
 int tile_elems(bool f32);
 
-/* SMALL: whole x in shared memory, one nnz-balanced row block per SM (spmv_kernels.cu) */
+/* SMALL: whole x in shared memory, one nnz-balanced row block per SM (spmv_small.cu) */
 struct DevSmall {
     const int *rowblk;    /* int[nblk + 1], first row of every row block */
     int nblk;
     int tile;             /* products a CTA can hold (entries) */
     int xpad;             /* elements reserved for x in shared memory */
     int ncols;
+    int use_tma;          /* x by TMA bulk copy when it is 16-byte aligned (B200_SPMV_SMALL_TMA) */
+    int pdl;              /* programmatic dependent launch (B200_SPMV_PDL) */
+    int cfg;              /* 0 = 1024 threads x 3 pairs per batch, 1 = 512 x 6 */
+    const uint16_t *col16;/* 0-based 16-bit copy of the columns (nullptr: the int32 columns as uploaded) */
 };
+void launch_small_col16(const int *col, uint16_t *col16, size_t n, cudaStream_t s);
 template <typename T>
 void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s);
 

@@ -55,12 +55,13 @@ y = torch.zeros(m.n, dtype=torch.float64, device="cuda")
 B = 12 * m.nnz + 4 * (m.n + 1) + 8 * ncols + 8 * m.n
 y_ref = None
 for cfg_full in configs:
-    # "cfg!NAME=V!NAME2=V2" adds B200_SPMV_PANEL_<NAME>=V to the environment of that upload
+    # "cfg!NAME=V!NAME2=V2" adds B200_SPMV_PANEL_<NAME>=V (B200_SPMV_<NAME>=V for SMALL_* names) to
+    # the environment of that upload
     cfg, *extras = cfg_full.split("!")
     env = {}
     for kv in extras:
         k, v = kv.split("=")
-        env["B200_SPMV_PANEL_" + k] = v
+        env[("B200_SPMV_" if k.startswith("SMALL_") else "B200_SPMV_PANEL_") + k] = v
     kernel = cfg
     if cfg.startswith("sell:"):
         kernel = "sell"

@@ -1016,17 +1016,20 @@ def test_vector_pinned_at_both_ends_with_a_pageable_hole_takes_the_bounce_buffer
     dict(n=3000, ncols=70000, mean=60, fits=False),         # x does not fit: falls back
     dict(n=40, ncols=5000, mean=60000, fits=False),         # rows longer than any tile: falls back
 ])
-def test_small_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape):
+@pytest.mark.parametrize("env", [{}, {"B200_SPMV_SMALL_COL16": 0}, {"B200_SPMV_SMALL_CFG": 1},
+                                 {"B200_SPMV_SMALL_TMA": 0, "B200_SPMV_SMALL_CFG": 1, "B200_SPMV_SMALL_COL16": 0}])
+def test_small_kernel_bit_exact_any_column_order(libspmv, oracle, dtype, sort, shape, env):
     """SMALL family (whole x in shared memory, products staged per row block, one thread per
     row adds left to right): bit-identical to the reference loop for sorted, unsorted and
-    repeated columns, empty rows, a row offset base > 1; matrices it cannot hold fall back to
-    the automatic choice."""
+    repeated columns, empty rows, a row offset base > 1 -- with 16-bit or the uploaded 32-bit
+    columns, either thread geometry, x by TMA or by the cooperative loop; matrices it cannot
+    hold fall back to the automatic choice."""
     rng = np.random.default_rng(shape["n"] * 13 + shape["mean"])
     lens = rng.poisson(shape["mean"], shape["n"])
     lens[rng.random(shape["n"]) < 0.1] = 0
     a, c, rowstr, x = make_csr(rng, shape["n"], shape["ncols"], lens, dtype=dtype, sort=sort,
                                base=1 if shape["n"] < 1000 else 4)
-    m, y = _exec_resident(libspmv, a, x, rowstr, c, "small")
+    m, y = _exec_resident(libspmv, a, x, rowstr, c, "small", env)
     assert (m.kernel_name == "small") == shape["fits"], (m.kernel_name, m.ncols, m.nnz)
     assert np.array_equal(y, oracle.spmv(a, x, rowstr, c))
     m.release()
@@ -1042,5 +1045,11 @@ def test_small_family_is_the_automatic_choice_for_npb_class_a(libspmv, oracle, n
     dy = torch.zeros(m.n, dtype=torch.float64, device="cuda")
     for _ in range(3):                                   # back to back: dependent launches
         rm.exec(torch.from_numpy(x).cuda(), dy)
-    assert np.array_equal(dy.cpu().numpy(), oracle.spmv(m.a, x, m.rowstr, m.colidx))
+    y0 = oracle.spmv(m.a, x, m.rowstr, m.colidx)
+    assert np.array_equal(dy.cpu().numpy(), y0)
+    # x NOT 16-byte aligned: no TMA bulk copy, the cooperative loop brings x in
+    big = torch.from_numpy(np.concatenate([[0.0], x])).cuda()
+    dy.zero_()
+    rm.exec(big[1:], dy)
+    assert big[1:].data_ptr() % 16 == 8 and np.array_equal(dy.cpu().numpy(), y0)
     rm.release()
