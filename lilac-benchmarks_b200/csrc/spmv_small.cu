@@ -8,18 +8,27 @@
  * product rounded, every row added left to right from 0 -- for ANY column order.
  *
  * One wave, one CTA per SM, an nnz-balanced row block each (build_small_locked).  The CTA
- *  (1) requests the first two batches of its slice of the CSR arrays as uploaded (coalesced,
- *      read once) -- BEFORE griddepcontrol.wait: the matrix is immutable, so under
- *      programmatic dependent launch these loads fly while the kernel in front drains;
+ *  (1) requests the first two batches of its slice of the matrix -- the values as uploaded,
+ *      in pairs (one 128-bit load per two entries), the columns from a 16-bit 0-based copy
+ *      made at upload (one 32-bit load per two entries; 10 instead of 12 bytes per entry) --
+ *      BEFORE griddepcontrol.wait: the matrix is immutable, so under programmatic dependent
+ *      launch these loads fly while the kernel in front drains.  A block that starts or ends
+ *      on an odd entry walks the neighbour's entry of that pair too and never adds it;
  *  (2) brings x in with ONE TMA bulk copy per 64 KB (cp.async.bulk + mbarrier; SASS UBLKCP):
- *      no registers, no per-thread round trips -- the cooperative loop it replaces cost four
- *      L2 latencies for class A's 112 KB; x vectors that are not 16-byte aligned still take
- *      that loop;
+ *      no registers, no per-thread round trips; x vectors that are not 16-byte aligned take a
+ *      cooperative loop instead;
  *  (3) forms the products with every thread, x gathered from shared memory, into a
  *      shared-memory tile, the next batch always requested before the current one is used;
  *  (4) adds each row's products left to right, one thread per row.
  * Only (4) is serial, and its chain is the longest row -- against one lane walking loads,
  * gathers and additions of whole rows in the panel kernels.
+ *
+ * Measured (launches from a C loop, profiles/r02_run40 / run42 / run44): class A 15.2 us on the
+ * panel layout -> 8.4 us (scalar loads, cooperative x) -> 8.3 us (TMA x: the x round trips
+ * were not the limit) -> 7.7 us (pairs + 16-bit columns: the ncu capture r02_run43 showed 26 %
+ * of the stall samples in the load/store queue -- 24 scalar loads per thread); classes W / S
+ * 4.3 / 3.0-3.8 us.  What is left for class A: 147 CTAs x (112 KB of x + 126 KB of matrix)
+ * = 35 MB through the L2 per launch, and the serial additions of the longest row.
  */
 #include "panel_common.cuh"
 
