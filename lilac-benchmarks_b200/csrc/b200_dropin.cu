@@ -879,8 +879,8 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
             x_alias = (const char *)e.h_x_alias;
         }
     }
-    /* y: device -> host (gpu.c:285).  The PANEL kernels store y coalesced, so they write
-     * straight into pinned host memory (the caller's, else the bounce buffer). */
+    /* y: device -> host (gpu.c:285).  The PANEL and SMALL kernels store y coalesced, so they
+     * write straight into pinned host memory (the caller's, else the bounce buffer). */
     char *y_alias = y_avoid ? nullptr : (char *)pinned_device_alias(ov, (size_t)n * es);
     const bool y_direct = y_alias != nullptr;
     char *y_host = y_direct ? (char *)ov : (char *)e.h_y;
@@ -968,7 +968,7 @@ static CallResult run_call(CacheEntry &e, void *ov, const void *iv, int n, int d
         const bool timed = g_time_kernels && timed_part < 0;
         if (timed) { CUDA_OK(cudaEventRecord(pt.ctx->ev0, s)); timed_part = p; }
         char *y_target = nullptr;
-        if (g_zero_copy && pt.m->kernel == B200_KERNEL_PANEL && y_alias)
+        if (g_zero_copy && (pt.m->kernel == B200_KERNEL_PANEL || pt.m->kernel == B200_KERNEL_SMALL) && y_alias)
             y_target = y_alias + (size_t)pt.row_lo * es;
         if (overlap) {
             SliceFlags sf = {pt.d_flags, epoch, e.x_chunk_cols, e.x_nchunks, &g_probe->x_timed_out, g_x_timeout_ns,

@@ -134,7 +134,7 @@ static int kernel_from_env(int requested)
     if (!strcmp(v, "sell")) return B200_KERNEL_SELL;
     if (!strcmp(v, "small")) return B200_KERNEL_SMALL;
     if (!strcmp(v, "auto")) return B200_KERNEL_AUTO;
-    die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|sell|merge", v);
+    die("B200_SPMV_KERNEL=%s is not one of auto|ordered|vector|panel|sell|merge|small", v);
     return 0;
 }
 
@@ -617,7 +617,7 @@ static bool build_small_locked(b200_matrix *m, const int *rowstr)
     const int xpad = (m->ncols + 3) & ~3;
     const size_t x_bytes = (size_t)xpad * es;
     if (x_bytes + 4096 > kSmemMax) return false;
-    const long long cap = (long long)((kSmemMax - x_bytes - 256) / es);
+    const long long cap = (long long)((kSmemMax - x_bytes - 512) / es);   /* header, pair slack */
     const int sms = m->ctx->sm_count;
     long long tile = std::max<long long>((m->nnz + sms - 1) / sms, m->scan.max_len);
     tile = std::max<long long>(tile, 64);
@@ -980,11 +980,13 @@ extern "C" int b200_spmv_exec_pushed(b200_matrix *m, void *d_y, void *stream, vo
 }
 
 /* y = A x and, in the same launch, partial[b] = (share of CTA b of) dotv . y for the first
- * b200_spmv_dot_partials(m) entries of `partial`.  Only the paired PANEL kernel has the
- * fused epilogue; returns -1 without launching otherwise. */
+ * b200_spmv_dot_partials(m) entries of `partial`.  The paired PANEL kernel and the SMALL
+ * kernel have the fused epilogue; returns -1 without launching otherwise. */
 extern "C" int b200_spmv_dot_partials(const b200_matrix *m)
 {
-    return (m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 0 && m->dtype == B200_F64) ? m->panel.nblk : 0;
+    if (m->dtype != B200_F64) return 0;
+    if (m->kernel == B200_KERNEL_SMALL) return m->small_.nblk;
+    return (m->kernel == B200_KERNEL_PANEL && m->panel.fmt == 0) ? m->panel.nblk : 0;
 }
 
 extern "C" int b200_spmv_exec_dot(b200_matrix *m, const void *d_x, void *d_y, const void *d_dotv,
@@ -993,8 +995,12 @@ extern "C" int b200_spmv_exec_dot(b200_matrix *m, const void *d_x, void *d_y, co
     if (!m) die("b200_spmv_exec_dot: null matrix");
     if (b200_spmv_dot_partials(m) <= 0) return -1;
     DeviceScope scope(m->device);
-    launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, (cudaStream_t)stream,
-                         (const double *)d_dotv, (double *)d_partial);
+    if (m->kernel == B200_KERNEL_SMALL)
+        launch_small<double>(m->small_, m->dev, (const double *)d_x, (double *)d_y, (cudaStream_t)stream,
+                             (const double *)d_dotv, (double *)d_partial);
+    else
+        launch_panel<double>(m->panel, (const double *)d_x, (double *)d_y, (cudaStream_t)stream,
+                             (const double *)d_dotv, (double *)d_partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) die("kernel launch failed: %s", cudaGetErrorString(e));
     return 1;

@@ -65,8 +65,10 @@ struct DevSmall {
     const uint16_t *col16;/* 0-based 16-bit copy of the columns (nullptr: the int32 columns as uploaded) */
 };
 void launch_small_col16(const int *col, uint16_t *col16, size_t n, cudaStream_t s);
+/* dotv != nullptr: dot_partial[b] = row block b's share of dotv . y, b < sm.nblk (fixed order) */
 template <typename T>
-void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s);
+void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s,
+                  const T *dotv = nullptr, T *dot_partial = nullptr);
 
 /* dst[0..bytes) = src[0..bytes): src is a device alias of pinned host memory,
  * so the loads travel over PCIe; runs on the SMs, in stream order */

@@ -34,6 +34,9 @@
 
 namespace b200 {
 
+/* dynamic shared memory: [0, 16) the x barrier, [16, 272) 32 warp sums, then x, then the products */
+constexpr int kSmallHeader = 16 + 32 * 8;
+
 /* column pairs: int2 of the 1-based columns as uploaded, or ushort2 of the 0-based 16-bit
  * private copy (x fits shared memory, so there are fewer than 65 536 columns) */
 template <typename CT> struct ColPair;
@@ -83,13 +86,15 @@ template <typename T, typename CT, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS, 1)
 spmv_small_kernel(const T *__restrict__ val, const CT *__restrict__ col,
                   const int *__restrict__ rowptr, const int *__restrict__ rowblk,
-                  const T *__restrict__ x, T *__restrict__ y, int ncols, int xpad, int use_tma)
+                  const T *__restrict__ x, T *__restrict__ y, int ncols, int xpad, int use_tma,
+                  const T *__restrict__ dotv, T *__restrict__ dot_partial)
 {
     using P2 = typename PairT<T>::type;
     using C2 = typename ColPair<CT>::type;
     extern __shared__ __align__(16) unsigned char small_smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(small_smem);          /* 16 bytes reserved */
-    T *xs = reinterpret_cast<T *>(small_smem + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(small_smem);          /* header: barrier, warp sums */
+    T *red = reinterpret_cast<T *>(small_smem + 16);                   /* [32] */
+    T *xs = reinterpret_cast<T *>(small_smem + kSmallHeader);
     T *prod = xs + xpad;                                               /* 16-byte aligned: xpad % 4 == 0 */
     constexpr int STEP = THREADS * U;
     /* a kernel behind this one in the stream may start its CTAs as ours finish */
@@ -143,24 +148,41 @@ spmv_small_kernel(const T *__restrict__ val, const CT *__restrict__ col,
         small_load<T, CT, THREADS, U>(b, v2, c2, p0 + 3 * STEP, np);
     }
     __syncthreads();
+    T dacc = (T)0;
     for (int r = r0 + tid; r < r1; r += THREADS) {
         const int s = __ldg(rowptr + r) - base, e = __ldg(rowptr + r + 1) - base;
         T acc = (T)0;
 #pragma unroll 8
         for (int k = s; k < e; ++k) acc = padd(acc, prod[k]);
         y[r] = acc;
+        if (dotv) dacc += acc * dotv[r];
+    }
+    /* optionally the block's share of dotv . y on the way out (NPB conj_grad's d = p.q,
+     * cg.f:573-576, as the PANEL epilogue): fixed order -- per-thread stride, xor-shuffle tree,
+     * warp sums left to right --, the same result on every launch */
+    if (dotv) {                                           /* block-uniform */
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+        if ((tid & 31) == 0) red[tid >> 5] = dacc;
+        __syncthreads();
+        if (tid == 0) {
+            T tot = (T)0;
+            for (int w = 0; w < THREADS / 32; ++w) tot += red[w];
+            dot_partial[blockIdx.x] = tot;
+        }
     }
 }
 
 template <typename T, typename CT, int THREADS, int U>
-static void launch_small_cfg(const DevSmall &sm, const DevCsr &m, const CT *col, const T *x, T *y, cudaStream_t s)
+static void launch_small_cfg(const DevSmall &sm, const DevCsr &m, const CT *col, const T *x, T *y, cudaStream_t s,
+                             const T *dotv, T *dot_partial)
 {
     static unsigned attr_mask = 0;
     if (!attr_done(&attr_mask))
         cudaFuncSetAttribute(spmv_small_kernel<T, CT, THREADS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024);
     /* + 4: the two entries of the neighbouring blocks that whole pairs may bring along */
-    const size_t smem = 16 + ((size_t)sm.xpad + (size_t)sm.tile + 4) * sizeof(T);
+    const size_t smem = kSmallHeader + ((size_t)sm.xpad + (size_t)sm.tile + 4) * sizeof(T);
     const int use_tma = sm.use_tma && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)sm.nblk);
@@ -176,14 +198,16 @@ static void launch_small_cfg(const DevSmall &sm, const DevCsr &m, const CT *col,
     if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
     cfg.numAttrs = (cap == cudaStreamCaptureStatusNone && sm.pdl) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, spmv_small_kernel<T, CT, THREADS, U>, static_cast<const T *>(m.val), col,
-                       (const int *)m.rowptr, (const int *)sm.rowblk, x, y, sm.ncols, sm.xpad, use_tma);
+                       (const int *)m.rowptr, (const int *)sm.rowblk, x, y, sm.ncols, sm.xpad, use_tma,
+                       dotv, dot_partial);
 }
 
 template <typename T, typename CT>
-static void launch_small_cols(const DevSmall &sm, const DevCsr &m, const CT *col, const T *x, T *y, cudaStream_t s)
+static void launch_small_cols(const DevSmall &sm, const DevCsr &m, const CT *col, const T *x, T *y, cudaStream_t s,
+                              const T *dotv, T *dot_partial)
 {
-    if (sm.cfg & 1) launch_small_cfg<T, CT, 512, 6>(sm, m, col, x, y, s);
-    else            launch_small_cfg<T, CT, 1024, 3>(sm, m, col, x, y, s);
+    if (sm.cfg & 1) launch_small_cfg<T, CT, 512, 6>(sm, m, col, x, y, s, dotv, dot_partial);
+    else            launch_small_cfg<T, CT, 1024, 3>(sm, m, col, x, y, s, dotv, dot_partial);
 }
 
 /* 16-bit 0-based copy of the columns, padding included (upload) */
@@ -200,13 +224,16 @@ void launch_small_col16(const int *col, uint16_t *col16, size_t n, cudaStream_t 
 }
 
 template <typename T>
-void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s)
+void launch_small(const DevSmall &sm, const DevCsr &m, const T *x, T *y, cudaStream_t s, const T *dotv,
+                  T *dot_partial)
 {
     if (sm.nblk <= 0) return;
-    if (sm.col16) launch_small_cols<T, uint16_t>(sm, m, sm.col16, x, y, s);
-    else          launch_small_cols<T, int>(sm, m, (const int *)m.col, x, y, s);
+    if (sm.col16) launch_small_cols<T, uint16_t>(sm, m, sm.col16, x, y, s, dotv, dot_partial);
+    else          launch_small_cols<T, int>(sm, m, (const int *)m.col, x, y, s, dotv, dot_partial);
 }
-template void launch_small<double>(const DevSmall &, const DevCsr &, const double *, double *, cudaStream_t);
-template void launch_small<float>(const DevSmall &, const DevCsr &, const float *, float *, cudaStream_t);
+template void launch_small<double>(const DevSmall &, const DevCsr &, const double *, double *, cudaStream_t,
+                                   const double *, double *);
+template void launch_small<float>(const DevSmall &, const DevCsr &, const float *, float *, cudaStream_t,
+                                  const float *, float *);
 
 }  // namespace b200

@@ -73,6 +73,10 @@ def lib():
     L.b200_spmv_exec_pushed.restype = c_int
     L.b200_spmv_can_push.argtypes = [c_void_p]
     L.b200_spmv_can_push.restype = c_int
+    L.b200_spmv_dot_partials.argtypes = [c_void_p]
+    L.b200_spmv_dot_partials.restype = c_int
+    L.b200_spmv_exec_dot.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.b200_spmv_exec_dot.restype = c_int
     L.b200_spmv_upload_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
     L.b200_spmv_upload_device.restype = c_void_p
     L.b200_spmv_device.argtypes = [c_void_p]
@@ -286,6 +290,7 @@ class ResidentMatrix:
         self.device = L.b200_spmv_device(self._h)
         self.waits_in_kernel = bool(L.b200_spmv_waits_in_kernel(self._h))
         self.can_push = bool(L.b200_spmv_can_push(self._h))
+        self.dot_partials = L.b200_spmv_dot_partials(self._h)
 
     def exec_sliced_ptr(self, d_x, d_y, stream, flags, epoch, cols_per_rank, nranks):
         """Product on an x that is still arriving slice by slice (include/b200_peer.h);
@@ -310,6 +315,23 @@ class ResidentMatrix:
         assert x.is_cuda and y.is_cuda and x.is_contiguous() and y.is_contiguous()
         assert x.numel() >= self.ncols and y.numel() >= self.rows
         return self.exec_ptr(x.data_ptr(), y.data_ptr(), stream)
+
+    def exec_dot(self, x, y, dotv, stream=None):
+        """y = A x and, in the same launch, the per-row-block shares of dotv . y (their sum, in
+        index order, is the dot product; fixed reduction order).  Returns the partials tensor,
+        or None if this matrix's kernel has no fused epilogue (nothing is launched)."""
+        import torch
+        if self.dot_partials <= 0:
+            return None
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        assert x.is_cuda and y.is_cuda and dotv.is_cuda and dotv.numel() >= self.rows
+        part = torch.zeros(self.dot_partials, dtype=torch.float64, device=x.device)
+        rc = lib().b200_spmv_exec_dot(self._h, c_void_p(x.data_ptr()), c_void_p(y.data_ptr()),
+                                      c_void_p(dotv.data_ptr()), c_void_p(part.data_ptr()), c_void_p(stream))
+        if rc != 1:
+            raise RuntimeError("b200_spmv_exec_dot refused a matrix that reported dot partials")
+        return part
 
     def npb_cg_device(self, nonzer, niter, shift, use_graph=True):
         """Whole NPB CG benchmark with every vector resident in HBM (include/b200_cg.h)."""

@@ -1053,3 +1053,28 @@ def test_small_family_is_the_automatic_choice_for_npb_class_a(libspmv, oracle, n
     rm.exec(big[1:], dy)
     assert big[1:].data_ptr() % 16 == 8 and np.array_equal(dy.cpu().numpy(), y0)
     rm.release()
+
+
+@pytest.mark.parametrize("cls,kernel", [("A", "auto"), ("W", "auto"), ("W", "panel"), ("B", "auto")])
+def test_fused_dot_epilogue(libspmv, oracle, npb, cls, kernel):
+    """b200_spmv_exec_dot (NPB conj_grad's d = p.q inside the product, cg.f:573-576): y is the
+    same bits as the plain product, the row-block partials add up to dotv . y, and the fixed
+    reduction order gives the same partials on every launch -- SMALL and paired PANEL kernels."""
+    import torch
+    m = npb.NpbMatrix(cls)
+    rm = libspmv.ResidentMatrix(m.a, m.rowstr, m.colidx, kernel=kernel)
+    assert rm.kernel_name == ("panel" if kernel == "panel" or cls == "B" else "small")
+    assert rm.dot_partials > 0
+    rng = np.random.default_rng(17)
+    x, p = rng.standard_normal(m.n), rng.standard_normal(m.n)
+    dx, dp = torch.from_numpy(x).cuda(), torch.from_numpy(p).cuda()
+    dy = torch.zeros(m.n, dtype=torch.float64, device="cuda")
+    part = rm.exec_dot(dx, dy, dp)
+    y0 = oracle.spmv(m.a, x, m.rowstr, m.colidx, omp=True)
+    assert np.array_equal(dy.cpu().numpy(), y0)
+    ref = float(np.dot(p, y0))
+    scale = float(np.dot(np.abs(p), np.abs(y0)))
+    assert abs(float(part.cpu().numpy().sum()) - ref) <= 1e-13 * scale
+    part2 = rm.exec_dot(dx, dy, dp)
+    assert torch.equal(part, part2)
+    rm.release()
